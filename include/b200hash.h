@@ -1,0 +1,119 @@
+/*
+ * b200hash.h -- C ABI of libb200hash.so: batched SHA-256 + MD5 content hashing on NVIDIA B200 (sm_100a).
+ *
+ * The reference (modal-labs/modal-client) has no FFI for this path: its seam is a set of Python
+ * module-level functions that call hashlib.  Each entry point below names the reference call site(s)
+ * it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub a
+ * maintainer would add to py/modal/_utils/hash_utils.py / blob_utils.py, and the cgo stub for go/blob.go.
+ *
+ * Conventions
+ *   - every function returning int returns 0 on success and a negative B200H_E_* code on failure;
+ *     b200h_last_error(ctx) gives a message (owned by the library, valid until the next call on ctx);
+ *   - no exceptions cross the boundary; the caller owns every buffer it passes;
+ *   - a context is bound to one CUDA device; calls on one context are serialised internally
+ *     (thread-safe, re-entrant across contexts); the caller's GIL is never needed;
+ *   - there is NO CPU fallback: without a usable CUDA device b200h_create fails with B200H_E_CUDA.
+ *   - digests are raw bytes: SHA-256 = 32 bytes (big-endian words, FIPS 180-4), MD5 = 16 bytes (RFC 1321).
+ */
+#ifndef B200HASH_H
+#define B200HASH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200H_SHA256 1u     /* compute SHA-256 */
+#define B200H_MD5 2u        /* compute MD5 */
+#define B200H_TRIM_ZEROS 4u /* hash the prefix up to the last non-zero byte (volumefs2 blocks) */
+
+#define B200H_OK 0
+#define B200H_E_INVALID (-1) /* bad argument */
+#define B200H_E_CUDA (-2)    /* CUDA runtime / driver error (no device, launch failure, ...) */
+#define B200H_E_NOMEM (-3)   /* host or device allocation failed */
+#define B200H_E_STATE (-4)   /* object used in the wrong state (e.g. update after final) */
+
+typedef struct b200h_ctx b200h_ctx;
+typedef struct b200h_stream b200h_stream;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+
+/* Bind a context to CUDA device `device`.  pinned_bytes / device_bytes size the host staging ring and
+ * the HBM staging buffers used by the *_host entry points (0 = defaults: 512 MiB pinned, 8 GiB HBM,
+ * both split in two for double buffering; they grow on demand for a message larger than half). */
+int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx** out);
+void b200h_destroy(b200h_ctx* ctx);
+/* ctx may be NULL: returns the message of the last failed b200h_create on this thread. */
+const char* b200h_last_error(b200h_ctx* ctx);
+const char* b200h_version(void);
+int b200h_device_count(void);
+
+/* Page-locked host memory the *_host entry points can DMA from directly (no staging copy). */
+void* b200h_host_alloc(b200h_ctx* ctx, size_t bytes);
+void b200h_host_free(b200h_ctx* ctx, void* p);
+
+/* ---- batch hashing ---------------------------------------------------------------------------- */
+
+/* Hash n independent messages that live in HOST memory; message i is base[offsets[i] .. +lengths[i]).
+ * (base may be NULL with absolute addresses in offsets[].)  Outputs (each may be NULL): sha256_out[n*32],
+ * md5_out[n*16], trimmed_len_out[n] (length actually hashed; == lengths[i] unless B200H_TRIM_ZEROS).
+ * Stages through pinned memory to HBM with cudaMemcpyAsync in double-buffered waves; blocks until the
+ * digests are in the output arrays.
+ * Replaces: hashlib in hash_utils.get_upload_hashes (py/modal/_utils/hash_utils.py:68-101) as called per
+ * payload from blob_utils.py:345 (map pump) and per file from blob_utils.py:459-474 (FileUploadSpec);
+ * with B200H_TRIM_ZEROS: _find_end_of_block + _hash_range_sha256 (blob_utils.py:640-705);
+ * md5.Sum/sha256.Sum256 in go/blob.go:51-52. */
+int b200h_hash_batch_host(b200h_ctx* ctx, const uint8_t* base, const uint64_t* offsets, const uint64_t* lengths,
+                          uint64_t n, uint32_t flags, uint8_t* sha256_out, uint8_t* md5_out,
+                          uint64_t* trimmed_len_out);
+
+/* Same, but every pointer is a DEVICE pointer on ctx's device and the call only enqueues work on
+ * `cuda_stream` (a cudaStream_t; NULL = the context's compute stream).  d_sha256/d_md5 must be 16-byte
+ * aligned.  This is the HBM-resident path the roofline is quoted on. */
+int b200h_hash_batch_device(b200h_ctx* ctx, const void* d_base, const uint64_t* d_offsets, const uint64_t* d_lengths,
+                            uint64_t n, uint32_t flags, void* d_sha256, void* d_md5, uint64_t* d_trimmed_len,
+                            void* cuda_stream);
+
+/* Split one host buffer into ceil(len/part_len) fixed-size parts and hash each (the last may be short).
+ * etag_md5_out (may be NULL) = MD5 over the concatenated raw part MD5s, computed on the device
+ * (requires B200H_MD5).  Returns the number of parts through *nparts_out.
+ * Replaces: the per-8MiB-block loop of _gather_blocks (blob_utils.py:622-645, with B200H_TRIM_ZEROS) and
+ * the per-part MD5 + md5(concat) ETag of perform_multipart_upload (blob_utils.py:194-219,
+ * bytes_io_segment_payload.py:58,102). */
+int b200h_hash_fixed_parts(b200h_ctx* ctx, const uint8_t* base, uint64_t len, uint64_t part_len, uint32_t flags,
+                           uint8_t* sha256_out, uint8_t* md5_out, uint64_t* trimmed_len_out,
+                           uint8_t etag_md5_out[16], uint64_t* nparts_out);
+
+/* ---- streaming single message (hashlib-object shaped) ------------------------------------------- */
+
+/* Incremental digest of ONE message fed in arbitrary pieces with bounded memory; the chaining state
+ * stays on the device between updates.  A single message is a serial Merkle-Damgard chain, so this is
+ * latency-bound by construction -- use the batch entry points for throughput.
+ * Replaces: hashlib objects in hash_utils._update over a BinaryIO (hash_utils.py:18-29) and
+ * BytesIOSegmentPayload._md5_checksum (bytes_io_segment_payload.py:58,102,79-80). */
+int b200h_stream_new(b200h_ctx* ctx, uint32_t flags, b200h_stream** out);
+int b200h_stream_update(b200h_stream* s, const uint8_t* data, uint64_t len);
+/* Non-destructive: may be called repeatedly and interleaved with further updates (like hashlib.digest()). */
+int b200h_stream_digest(b200h_stream* s, uint8_t sha256_out[32], uint8_t md5_out[16]);
+int b200h_stream_reset(b200h_stream* s);
+void b200h_stream_free(b200h_stream* s);
+
+/* ---- utilities ---------------------------------------------------------------------------------- */
+
+/* Counter-based synthetic bytes on the device (bench / test data): d_dst[0..nbytes) = bytes
+ * [start, start+nbytes) of stream `seed`; d_dst 8-byte aligned, start a multiple of 8. */
+int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64_t seed, uint64_t start,
+                            void* cuda_stream);
+/* Kernels launched by this context so far (all kinds). */
+uint64_t b200h_launch_count(b200h_ctx* ctx);
+/* When enabled, every lane_hash launch is bracketed by CUDA events on its stream;
+ * b200h_profile_read synchronises and returns the accumulated device time and launch count, then clears. */
+int b200h_profile_enable(b200h_ctx* ctx, int on);
+int b200h_profile_read(b200h_ctx* ctx, double* hash_kernel_ms, uint64_t* hash_kernel_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200HASH_H */

@@ -1,0 +1,299 @@
+"""ctypes binding of libb200hash.so (C ABI: include/b200hash.h).
+
+There is deliberately no CPU fallback in this package: if the shared library is missing, or no B200
+is visible, every entry point raises ``B200HashError``.  ``build_library()`` (re)builds the .so in-tree
+with nvcc for sm_100a (cross-compiles without a GPU).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from typing import Sequence
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libb200hash.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+SHA256 = 1
+MD5 = 2
+TRIM_ZEROS = 4
+
+#: every symbol include/b200hash.h declares (tests check the .so exports all of them)
+ABI_SYMBOLS = (
+    "b200h_create", "b200h_destroy", "b200h_last_error", "b200h_version", "b200h_device_count",
+    "b200h_host_alloc", "b200h_host_free", "b200h_hash_batch_host", "b200h_hash_batch_device",
+    "b200h_hash_fixed_parts", "b200h_stream_new", "b200h_stream_update", "b200h_stream_digest",
+    "b200h_stream_reset", "b200h_stream_free", "b200h_fill_synth_device", "b200h_launch_count",
+    "b200h_profile_enable", "b200h_profile_read",
+)
+
+
+class B200HashError(RuntimeError):
+    """The CUDA library is missing or a GPU call failed.  Never swallowed, never replaced by CPU work."""
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, f) for f in ("b200hash_kernels.cu", "b200hash_api.cu", "b200hash_kernels.cuh")]
+    srcs.append(os.path.join(os.path.dirname(_PKG), "include", "b200hash.h"))
+    stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or out.returncode:
+            print(out.stdout, out.stderr)
+        if out.returncode:
+            raise B200HashError(f"building libb200hash.so failed:\n{out.stdout}\n{out.stderr}")
+    return LIB_PATH
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libb200hash.so and declare prototypes.  Works without a GPU (symbols only)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise B200HashError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  modal_client_b200 has no CPU fallback."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        vp, u64, u32, i32, sz = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_size_t
+        L.b200h_create.argtypes = [i32, sz, sz, ctypes.POINTER(vp)]
+        L.b200h_create.restype = i32
+        L.b200h_destroy.argtypes = [vp]
+        L.b200h_destroy.restype = None
+        L.b200h_last_error.argtypes = [vp]
+        L.b200h_last_error.restype = ctypes.c_char_p
+        L.b200h_version.argtypes = []
+        L.b200h_version.restype = ctypes.c_char_p
+        L.b200h_device_count.argtypes = []
+        L.b200h_device_count.restype = i32
+        L.b200h_host_alloc.argtypes = [vp, sz]
+        L.b200h_host_alloc.restype = vp
+        L.b200h_host_free.argtypes = [vp, vp]
+        L.b200h_host_free.restype = None
+        L.b200h_hash_batch_host.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, vp]
+        L.b200h_hash_batch_host.restype = i32
+        L.b200h_hash_batch_device.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, vp, vp]
+        L.b200h_hash_batch_device.restype = i32
+        L.b200h_hash_fixed_parts.argtypes = [vp, vp, u64, u64, u32, vp, vp, vp, vp, ctypes.POINTER(u64)]
+        L.b200h_hash_fixed_parts.restype = i32
+        L.b200h_stream_new.argtypes = [vp, u32, ctypes.POINTER(vp)]
+        L.b200h_stream_new.restype = i32
+        L.b200h_stream_update.argtypes = [vp, vp, u64]
+        L.b200h_stream_update.restype = i32
+        L.b200h_stream_digest.argtypes = [vp, vp, vp]
+        L.b200h_stream_digest.restype = i32
+        L.b200h_stream_reset.argtypes = [vp]
+        L.b200h_stream_reset.restype = i32
+        L.b200h_stream_free.argtypes = [vp]
+        L.b200h_stream_free.restype = None
+        L.b200h_fill_synth_device.argtypes = [vp, vp, u64, u64, u64, vp]
+        L.b200h_fill_synth_device.restype = i32
+        L.b200h_launch_count.argtypes = [vp]
+        L.b200h_launch_count.restype = u64
+        L.b200h_profile_enable.argtypes = [vp, i32]
+        L.b200h_profile_enable.restype = i32
+        L.b200h_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
+        L.b200h_profile_read.restype = i32
+        _lib = L
+        return L
+
+
+def _np_ptr(a: np.ndarray | None):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One libb200hash context bound to one GPU.  Thread-safe (calls serialise inside the library)."""
+
+    def __init__(self, device: int = 0, pinned_bytes: int = 0, device_bytes: int = 0):
+        self._L = load_library()
+        h = ctypes.c_void_p()
+        rc = self._L.b200h_create(device, pinned_bytes, device_bytes, ctypes.byref(h))
+        if rc != 0:
+            msg = (self._L.b200h_last_error(None) or b"").decode()
+            raise B200HashError(f"b200h_create(device={device}) failed ({rc}): {msg}")
+        self._h = h
+        self.device = device
+
+    # -- plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = (self._L.b200h_last_error(self._h) or b"").decode()
+            raise B200HashError(f"{what} failed ({rc}): {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200h_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.b200h_launch_count(self._h))
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._L.b200h_profile_enable(self._h, int(on)), "b200h_profile_enable")
+
+    def profile_read(self) -> tuple[float, int]:
+        ms, n = ctypes.c_double(), ctypes.c_uint64()
+        self._check(self._L.b200h_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)), "b200h_profile_read")
+        return ms.value, n.value
+
+    # -- pinned host memory
+    def host_alloc(self, nbytes: int) -> np.ndarray:
+        """uint8[nbytes] view of page-locked memory (freed with host_free)."""
+        p = self._L.b200h_host_alloc(self._h, nbytes)
+        if not p:
+            self._check(-3, "b200h_host_alloc")
+        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+        arr.flags.writeable = True
+        arr_base = arr  # keep ctypes buffer alive via arr.base
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr_base.ctypes.data] = p
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        p = getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
+        if p:
+            self._L.b200h_host_free(self._h, p)
+
+    # -- batch over host memory
+    def hash_batch_host(self, base, offsets, lengths, flags: int = SHA256 | MD5):
+        """base: uint8 ndarray / bytes-like / int address / None (absolute addresses in offsets).
+        -> (sha[n,32] | None, md5[n,16] | None, trimmed[n])"""
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        n = int(off.size)
+        assert ln.size == n
+        keep = None
+        if base is None:
+            bp = None
+        elif isinstance(base, int):
+            bp = ctypes.c_void_p(base)
+        elif isinstance(base, np.ndarray):
+            assert base.dtype == np.uint8 and base.flags.c_contiguous
+            bp = ctypes.c_void_p(base.ctypes.data)
+        else:
+            keep = np.frombuffer(base, dtype=np.uint8)
+            bp = ctypes.c_void_p(keep.ctypes.data) if keep.size else ctypes.c_void_p(off.ctypes.data)
+        sha = np.empty((n, 32), np.uint8) if flags & SHA256 else None
+        md5 = np.empty((n, 16), np.uint8) if flags & MD5 else None
+        trimmed = np.empty(n, np.uint64)
+        rc = self._L.b200h_hash_batch_host(self._h, bp, _np_ptr(off), _np_ptr(ln), n, flags, _np_ptr(sha),
+                                           _np_ptr(md5), _np_ptr(trimmed))
+        self._check(rc, "b200h_hash_batch_host")
+        del keep
+        return sha, md5, trimmed
+
+    def hash_buffers(self, bufs: Sequence, flags: int = SHA256 | MD5):
+        """Hash many separate bytes-like objects without packing them in Python: their addresses go to
+        the library as absolute offsets (base=NULL) and it gathers them into its pinned staging ring."""
+        views = [np.frombuffer(b, dtype=np.uint8) for b in bufs]
+        off = np.fromiter((v.ctypes.data if v.size else 0 for v in views), dtype=np.uint64, count=len(views))
+        ln = np.fromiter((v.size for v in views), dtype=np.uint64, count=len(views))
+        out = self.hash_batch_host(None, off, ln, flags)
+        del views
+        return out
+
+    # -- batch over device memory (raw pointers: torch tensors' data_ptr())
+    def hash_batch_device(self, d_base: int, d_offsets: int, d_lengths: int, n: int, flags: int, d_sha: int, d_md5: int,
+                          d_trimmed: int = 0, stream: int = 0):
+        rc = self._L.b200h_hash_batch_device(self._h, d_base, d_offsets, d_lengths, n, flags, d_sha or None,
+                                             d_md5 or None, d_trimmed or None, stream or None)
+        self._check(rc, "b200h_hash_batch_device")
+
+    def hash_fixed_parts(self, data, part_len: int, flags: int = SHA256 | MD5, want_etag: bool = False):
+        """-> (sha[np,32]|None, md5[np,16]|None, trimmed[np], etag bytes|None)"""
+        if isinstance(data, np.ndarray):
+            a = data
+        else:
+            a = np.frombuffer(data, dtype=np.uint8)
+        total = int(a.size)
+        nparts = -(-total // part_len) if total else 0
+        sha = np.empty((nparts, 32), np.uint8) if flags & SHA256 else None
+        md5 = np.empty((nparts, 16), np.uint8) if flags & MD5 else None
+        trimmed = np.empty(nparts, np.uint64)
+        etag = np.empty(16, np.uint8) if want_etag else None
+        got = ctypes.c_uint64()
+        bp = ctypes.c_void_p(a.ctypes.data) if total else None
+        rc = self._L.b200h_hash_fixed_parts(self._h, bp, total, part_len, flags, _np_ptr(sha), _np_ptr(md5),
+                                            _np_ptr(trimmed), _np_ptr(etag), ctypes.byref(got))
+        self._check(rc, "b200h_hash_fixed_parts")
+        assert got.value == nparts
+        return sha, md5, trimmed, (etag.tobytes() if want_etag else None)
+
+    def fill_synth_device(self, d_ptr: int, nbytes: int, seed: int, start: int = 0, stream: int = 0):
+        self._check(self._L.b200h_fill_synth_device(self._h, d_ptr, nbytes, seed, start, stream or None),
+                    "b200h_fill_synth_device")
+
+    def stream(self, flags: int = SHA256 | MD5) -> "DigestStream":
+        return DigestStream(self, flags)
+
+
+class DigestStream:
+    """hashlib-object shaped incremental digest (update / digest / reset); state lives on the GPU."""
+
+    def __init__(self, ctx: Context, flags: int):
+        self._ctx = ctx
+        self._flags = flags
+        h = ctypes.c_void_p()
+        ctx._check(ctx._L.b200h_stream_new(ctx._h, flags, ctypes.byref(h)), "b200h_stream_new")
+        self._h = h
+
+    def update(self, data) -> None:
+        v = np.frombuffer(data, dtype=np.uint8)
+        if v.size:
+            self._ctx._check(self._ctx._L.b200h_stream_update(self._h, ctypes.c_void_p(v.ctypes.data), v.size),
+                             "b200h_stream_update")
+
+    def digests(self) -> tuple[bytes | None, bytes | None]:
+        sha = np.empty(32, np.uint8)
+        md5 = np.empty(16, np.uint8)
+        self._ctx._check(self._ctx._L.b200h_stream_digest(self._h, _np_ptr(sha), _np_ptr(md5)), "b200h_stream_digest")
+        return (sha.tobytes() if self._flags & SHA256 else None, md5.tobytes() if self._flags & MD5 else None)
+
+    def reset(self) -> None:
+        self._ctx._check(self._ctx._L.b200h_stream_reset(self._h), "b200h_stream_reset")
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._ctx._L.b200h_stream_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default: dict[int, Context] = {}
+_default_lock = threading.Lock()
+
+
+def default_context(device: int | None = None) -> Context:
+    """Process-wide context per device (LOCAL_RANK picks the device under torchrun)."""
+    if device is None:
+        device = int(os.environ.get("B200H_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        ctx = _default.get(device)
+        if ctx is None:
+            ctx = _default[device] = Context(device)
+        return ctx

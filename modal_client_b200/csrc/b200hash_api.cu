@@ -1,0 +1,719 @@
+// b200hash_api.cu -- host side of libb200hash.so: the C ABI declared in include/b200hash.h.
+//
+// Owns the per-device context (streams, pinned staging ring, HBM wave buffers, grow-only scratch),
+// turns host batches into double-buffered waves (pack -> cudaMemcpyAsync -> trim/plan/lane_hash) and
+// implements the streaming (hashlib-object shaped) interface on top of the chaining-state kernel mode.
+// No CPU hashing exists in this library: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200hash.h"
+#include "b200hash_kernels.cuh"
+
+using namespace b200h;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Wave {
+    uint64_t i0, i1;    // message index range [i0, i1)
+    uint64_t src_lo;    // direct mode: host offset (relative to base) of the first byte copied
+    uint64_t bytes;     // bytes occupying the device wave buffer
+};
+
+}  // namespace
+
+struct b200h_ctx {
+    int device = 0;
+    std::mutex mu;
+    std::string err;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};    // H2D of a wave slot finished
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // kernels reading a wave slot finished
+    cudaEvent_t ev_pin[2] = {nullptr, nullptr};       // H2D out of a pinned slot finished
+    cudaEvent_t ev_scratch = nullptr;                 // last use of the shared scratch buffers
+    bool scratch_used = false;
+    uint8_t* pin[2] = {nullptr, nullptr};
+    size_t pin_cap = 0;  // per slot
+    uint8_t* dwave[2] = {nullptr, nullptr};
+    size_t dwave_cap = 0;  // per slot
+    size_t dwave_want = 0;
+    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small;
+    uint64_t* h_meta = nullptr;  // pinned: offsets then lengths
+    size_t h_meta_cap = 0;       // in uint64 elements
+    uint64_t launches = 0;
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    double prof_ms = 0.0;
+    uint64_t prof_n = 0;
+    int pack_threads = 1;
+};
+
+struct b200h_stream {
+    b200h_ctx* ctx = nullptr;
+    uint32_t flags = 0;
+    uint8_t* hbuf = nullptr;  // host accumulation buffer (cap bytes, multiple of 64)
+    size_t cap = 0;
+    size_t fill = 0;
+    uint8_t* d_buf = nullptr;      // device copy of hbuf
+    ChainState* d_state = nullptr; // [0] running state, [1] scratch copy for digest()
+    uint64_t* d_meta = nullptr;    // off, len
+    uint8_t* d_out = nullptr;      // 32 + 16
+    uint64_t total = 0;
+};
+
+namespace {
+
+int fail(b200h_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess) {                                                                           \
+            char b__[512];                                                                                  \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            cudaGetLastError();                                                                             \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? B200H_E_NOMEM : B200H_E_CUDA, b__);         \
+        }                                                                                                   \
+    } while (0)
+
+int ensure_dev(b200h_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    want = (want + 255) & ~size_t(255);
+    if (b.p) {
+        CU_TRY(ctx, cudaDeviceSynchronize());
+        CU_TRY(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    CU_TRY(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+int ensure_wave(b200h_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->dwave_cap) return 0;
+    // grow geometrically towards the configured wave size; beyond it only as far as one message needs
+    size_t want = std::max(bytes, std::min(ctx->dwave_want, std::max<size_t>(2 * ctx->dwave_cap, size_t(64) << 20)));
+    want = (want + 255) & ~size_t(255);
+    CU_TRY(ctx, cudaDeviceSynchronize());
+    for (int s = 0; s < 2; ++s) {
+        if (ctx->dwave[s]) CU_TRY(ctx, cudaFree(ctx->dwave[s]));
+        ctx->dwave[s] = nullptr;
+    }
+    ctx->dwave_cap = 0;
+    for (int s = 0; s < 2; ++s) CU_TRY(ctx, cudaMalloc(&ctx->dwave[s], want));
+    ctx->dwave_cap = want;
+    return 0;
+}
+
+int ensure_meta(b200h_ctx* ctx, size_t elems) {
+    if (elems <= ctx->h_meta_cap) return 0;
+    if (ctx->h_meta) CU_TRY(ctx, cudaFreeHost(ctx->h_meta));
+    ctx->h_meta = nullptr;
+    ctx->h_meta_cap = 0;
+    size_t want = std::max(elems, size_t(1) << 16);
+    CU_TRY(ctx, cudaHostAlloc(&ctx->h_meta, want * sizeof(uint64_t), cudaHostAllocDefault));
+    ctx->h_meta_cap = want;
+    return 0;
+}
+
+// lanes per warp: pack 32 messages per warp only when there are enough messages to fill the chip;
+// small batches spread one message per warp so every chain gets its own issue slots.
+int choose_lanes_per_warp(uint64_t n) {
+    const uint64_t target_warps = 148ull * 16ull;
+    uint64_t g = (n + target_warps - 1) / target_warps;
+    int lpw = 1;
+    while ((uint64_t)lpw < g && lpw < 32) lpw <<= 1;
+    return lpw;
+}
+
+int prof_begin(b200h_ctx* ctx, cudaStream_t st, cudaEvent_t* a, cudaEvent_t* b) {
+    *a = *b = nullptr;
+    if (!ctx->profiling) return 0;
+    CU_TRY(ctx, cudaEventCreate(a));
+    CU_TRY(ctx, cudaEventCreate(b));
+    CU_TRY(ctx, cudaEventRecord(*a, st));
+    return 0;
+}
+int prof_end(b200h_ctx* ctx, cudaStream_t st, cudaEvent_t a, cudaEvent_t b) {
+    if (!a) return 0;
+    CU_TRY(ctx, cudaEventRecord(b, st));
+    ctx->prof_events.emplace_back(a, b);
+    return 0;
+}
+
+// Enqueue trim -> plan -> lane_hash for n device-resident messages on `st`.  ctx->mu must be held.
+int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* d_off, const uint64_t* d_len,
+                         uint64_t n, uint32_t flags, uint8_t* d_sha, uint8_t* d_md5, uint64_t* d_trim_out,
+                         ChainState* d_state, cudaStream_t st) {
+    if (n == 0) return 0;
+    if (n > 0xffffffffull) return fail(ctx, B200H_E_INVALID, "batch larger than 2^32-1 messages");
+    uint32_t kflags = 0;
+    if (flags & B200H_SHA256) kflags |= F_SHA256;
+    if (flags & B200H_MD5) kflags |= F_MD5;
+    if (flags & 0x80000000u) kflags |= F_NO_FINAL;  // internal: continuation segment
+    if (!(kflags & (F_SHA256 | F_MD5))) return fail(ctx, B200H_E_INVALID, "flags select neither SHA256 nor MD5");
+
+    if (ctx->scratch_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
+    const uint64_t* len_used = d_len;
+    if (flags & B200H_TRIM_ZEROS) {
+        uint64_t* tbuf = d_trim_out;
+        if (!tbuf) {
+            if (int rc = ensure_dev(ctx, ctx->d_trim, n * sizeof(uint64_t))) return rc;
+            tbuf = (uint64_t*)ctx->d_trim.p;
+        }
+        ctx->launches += launch_trim(d_base, d_off, d_len, n, tbuf, st);
+        len_used = tbuf;
+    } else if (d_trim_out) {
+        CU_TRY(ctx, cudaMemcpyAsync(d_trim_out, d_len, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    }
+    const uint32_t* order = nullptr;
+    if (n > 1) {
+        if (int rc = ensure_dev(ctx, ctx->d_order, n * sizeof(uint32_t))) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_scratch, (2 * kPlanBuckets + 2) * sizeof(uint32_t))) return rc;
+        ctx->launches += launch_plan(len_used, n, (uint32_t*)ctx->d_order.p, (uint32_t*)ctx->d_scratch.p, st);
+        order = (const uint32_t*)ctx->d_order.p;
+    }
+    cudaEvent_t pa, pb;
+    if (int rc = prof_begin(ctx, st, &pa, &pb)) return rc;
+    ctx->launches += launch_lane_hash(d_base, d_off, len_used, order, n, kflags, choose_lanes_per_warp(n), d_sha,
+                                      d_md5, d_state, st);
+    if (int rc = prof_end(ctx, st, pa, pb)) return rc;
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_scratch, st));
+    ctx->scratch_used = true;
+    return 0;
+}
+
+// Copy the packed byte range [lo, hi) of a staged wave into dst (= pinned slot, dst[0] <-> packed byte lo).
+// doff[] are the packed offsets (ascending) of messages i0..i1 inside the wave.
+void pack_range(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint64_t* doff, uint64_t i0,
+                uint64_t i1, uint64_t lo, uint64_t hi, uint8_t* dst) {
+    // first message whose packed end is beyond lo
+    uint64_t a = i0, b = i1;
+    while (a < b) {
+        const uint64_t m = (a + b) / 2;
+        if (doff[m] + len[m] <= lo) a = m + 1;
+        else b = m;
+    }
+    for (uint64_t i = a; i < i1 && doff[i] < hi; ++i) {
+        const uint64_t s = std::max(doff[i], lo), e = std::min(doff[i] + len[i], hi);
+        if (e > s) memcpy(dst + (s - lo), base + off[i] + (s - doff[i]), (size_t)(e - s));
+    }
+}
+
+void pack_parallel(int threads, const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint64_t* doff,
+                   uint64_t i0, uint64_t i1, uint64_t lo, uint64_t hi, uint8_t* dst) {
+    const uint64_t bytes = hi - lo;
+    int t = (int)std::min<uint64_t>((uint64_t)threads, bytes / (4u << 20));
+    if (t <= 1) {
+        pack_range(base, off, len, doff, i0, i1, lo, hi, dst);
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve(t);
+    for (int k = 0; k < t; ++k) {
+        const uint64_t a = lo + bytes * k / t, b = lo + bytes * (k + 1) / t;
+        th.emplace_back([=] { pack_range(base, off, len, doff, i0, i1, a, b, dst + (a - lo)); });
+    }
+    for (auto& x : th) x.join();
+}
+
+int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n,
+                         uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, uint64_t* trim_out, uint8_t* etag_out) {
+    if (n == 0) return 0;
+    if (!off || !len) return fail(ctx, B200H_E_INVALID, "offsets/lengths must not be NULL");
+    if (!(flags & (B200H_SHA256 | B200H_MD5))) return fail(ctx, B200H_E_INVALID, "flags select neither SHA256 nor MD5");
+    if (etag_out && !(flags & B200H_MD5)) return fail(ctx, B200H_E_INVALID, "etag requires B200H_MD5");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+
+    // Page-locked source?  Then DMA straight from the caller's memory, no staging copy.
+    bool direct = false;
+    if (base) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, base) == cudaSuccess) direct = (at.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+    }
+
+    if (int rc = ensure_meta(ctx, 2 * n)) return rc;
+    uint64_t* doff = ctx->h_meta;      // device-relative offsets
+    uint64_t* hlen = ctx->h_meta + n;  // lengths (pinned copy)
+    memcpy(hlen, len, n * sizeof(uint64_t));
+
+    // ---- carve the batch into waves that fit one HBM wave slot
+    size_t cap = std::max(ctx->dwave_cap, ctx->dwave_want);
+    std::vector<Wave> waves;
+    {
+        uint64_t i = 0;
+        while (i < n) {
+            Wave w{i, i, 0, 0};
+            if (direct) {
+                uint64_t lo = off[i], hi = off[i] + len[i];
+                uint64_t j = i + 1;
+                for (; j < n; ++j) {
+                    const uint64_t nlo = std::min(lo, off[j]), nhi = std::max(hi, off[j] + len[j]);
+                    if (nhi - (nlo & ~15ull) > cap) break;
+                    lo = nlo;
+                    hi = nhi;
+                }
+                w.i1 = j;
+                w.src_lo = lo & ~15ull;  // keep the 16-byte phase of every message
+                w.bytes = hi - w.src_lo;
+                for (uint64_t k = i; k < j; ++k) doff[k] = off[k] - w.src_lo;
+            } else {
+                uint64_t used = 0;
+                uint64_t j = i;
+                for (; j < n; ++j) {
+                    const uint64_t need = (len[j] + 15) & ~15ull;
+                    if (j > i && used + need > cap) break;
+                    doff[j] = used;
+                    used += need;
+                }
+                w.i1 = j;
+                w.bytes = used;
+            }
+            waves.push_back(w);
+            i = w.i1;
+        }
+    }
+    size_t need_wave = 16;
+    for (auto& w : waves) need_wave = std::max<size_t>(need_wave, w.bytes);
+    if (int rc = ensure_wave(ctx, need_wave)) return rc;
+
+    if (int rc = ensure_dev(ctx, ctx->d_off, n * sizeof(uint64_t))) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_len, n * sizeof(uint64_t))) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_trim, n * sizeof(uint64_t))) return rc;
+    if (flags & B200H_SHA256)
+        if (int rc = ensure_dev(ctx, ctx->d_sha, n * 32)) return rc;
+    if (flags & B200H_MD5)
+        if (int rc = ensure_dev(ctx, ctx->d_md5, n * 16 + 16)) return rc;
+    uint64_t* d_off = (uint64_t*)ctx->d_off.p;
+    uint64_t* d_len = (uint64_t*)ctx->d_len.p;
+    uint64_t* d_trim = (uint64_t*)ctx->d_trim.p;
+    uint8_t* d_sha = (flags & B200H_SHA256) ? (uint8_t*)ctx->d_sha.p : nullptr;
+    uint8_t* d_md5 = (flags & B200H_MD5) ? (uint8_t*)ctx->d_md5.p : nullptr;
+
+    CU_TRY(ctx, cudaMemcpyAsync(d_off, doff, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_comp));
+    CU_TRY(ctx, cudaMemcpyAsync(d_len, hlen, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_comp));
+
+    bool pin_used[2] = {false, false};
+    int pin_slot = 0;
+    for (size_t wi = 0; wi < waves.size(); ++wi) {
+        const Wave& w = waves[wi];
+        const int slot = (int)(wi & 1);
+        if (wi >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_copy, ctx->ev_consumed[slot], 0));
+        if (direct) {
+            if (w.bytes)
+                CU_TRY(ctx, cudaMemcpyAsync(ctx->dwave[slot], base + w.src_lo, w.bytes, cudaMemcpyHostToDevice,
+                                            ctx->s_copy));
+        } else {
+            for (uint64_t lo = 0; lo < w.bytes; lo += ctx->pin_cap) {
+                const uint64_t hi = std::min<uint64_t>(w.bytes, lo + ctx->pin_cap);
+                if (pin_used[pin_slot]) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_pin[pin_slot]));
+                pack_parallel(ctx->pack_threads, base, off, len, doff, w.i0, w.i1, lo, hi, ctx->pin[pin_slot]);
+                CU_TRY(ctx, cudaMemcpyAsync(ctx->dwave[slot] + lo, ctx->pin[pin_slot], hi - lo, cudaMemcpyHostToDevice,
+                                            ctx->s_copy));
+                CU_TRY(ctx, cudaEventRecord(ctx->ev_pin[pin_slot], ctx->s_copy));
+                pin_used[pin_slot] = true;
+                pin_slot ^= 1;
+            }
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->s_copy));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_copied[slot], 0));
+        const uint64_t cnt = w.i1 - w.i0;
+        if (int rc = enqueue_device_batch(ctx, ctx->dwave[slot], d_off + w.i0, d_len + w.i0, cnt, flags,
+                                          d_sha ? d_sha + 32 * w.i0 : nullptr, d_md5 ? d_md5 + 16 * w.i0 : nullptr,
+                                          d_trim + w.i0, nullptr, ctx->s_comp))
+            return rc;
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[slot], ctx->s_comp));
+    }
+
+    uint8_t* d_etag = nullptr;
+    if (etag_out) {
+        // MD5 over the concatenated raw part digests, still on the device (blob_utils.py:216-219)
+        if (int rc = ensure_dev(ctx, ctx->d_small, 64)) return rc;
+        uint64_t meta[2] = {0, n * 16};
+        uint64_t* d_meta = (uint64_t*)ctx->d_small.p;
+        d_etag = (uint8_t*)ctx->d_small.p + 32;
+        CU_TRY(ctx, cudaMemcpyAsync(d_meta, meta, sizeof meta, cudaMemcpyHostToDevice, ctx->s_comp));
+        if (int rc = enqueue_device_batch(ctx, d_md5, d_meta, d_meta + 1, 1, B200H_MD5, nullptr, d_etag, nullptr,
+                                          nullptr, ctx->s_comp))
+            return rc;
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_comp));
+    if (sha_out && d_sha) CU_TRY(ctx, cudaMemcpy(sha_out, d_sha, n * 32, cudaMemcpyDeviceToHost));
+    if (md5_out && d_md5) CU_TRY(ctx, cudaMemcpy(md5_out, d_md5, n * 16, cudaMemcpyDeviceToHost));
+    if (trim_out) CU_TRY(ctx, cudaMemcpy(trim_out, d_trim, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (etag_out) CU_TRY(ctx, cudaMemcpy(etag_out, d_etag, 16, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+
+extern "C" {
+
+const char* b200h_version(void) { return kernel_build_info(); }
+
+int b200h_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* b200h_last_error(b200h_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx** out) {
+    if (!out) return fail(nullptr, B200H_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, B200H_E_CUDA,
+                    std::string("no usable CUDA device (libb200hash has no CPU fallback): ") + cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, B200H_E_INVALID, "device index out of range");
+    b200h_ctx* ctx = new (std::nothrow) b200h_ctx();
+    if (!ctx) return fail(nullptr, B200H_E_NOMEM, "out of host memory");
+    ctx->device = device;
+    auto bail = [&](int rc) {
+        g_create_error = ctx->err;
+        b200h_destroy(ctx);
+        return rc;
+    };
+#define CU_INIT(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call " failed: ") + cudaGetErrorString(e__);                   \
+            cudaGetLastError();                                                                    \
+            return bail(e__ == cudaErrorMemoryAllocation ? B200H_E_NOMEM : B200H_E_CUDA);          \
+        }                                                                                          \
+    } while (0)
+    CU_INIT(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_INIT(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        ctx->err = "device is not Blackwell-class (kernels are built for sm_100a only)";
+        return bail(B200H_E_CUDA);
+    }
+    CU_INIT(configure_kernels());
+    CU_INIT(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+    CU_INIT(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+        CU_INIT(cudaEventCreateWithFlags(&ctx->ev_copied[s], cudaEventDisableTiming));
+        CU_INIT(cudaEventCreateWithFlags(&ctx->ev_consumed[s], cudaEventDisableTiming));
+        CU_INIT(cudaEventCreateWithFlags(&ctx->ev_pin[s], cudaEventDisableTiming));
+    }
+    CU_INIT(cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming));
+    if (pinned_bytes == 0) pinned_bytes = size_t(512) << 20;
+    if (device_bytes == 0) device_bytes = size_t(8) << 30;
+    ctx->pin_cap = std::max<size_t>((pinned_bytes / 2) & ~size_t(4095), 1 << 20);
+    ctx->dwave_want = std::max<size_t>((device_bytes / 2) & ~size_t(255), 1 << 20);
+    for (int s = 0; s < 2; ++s) CU_INIT(cudaHostAlloc(&ctx->pin[s], ctx->pin_cap, cudaHostAllocDefault));
+    unsigned hc = std::thread::hardware_concurrency();
+    ctx->pack_threads = (int)std::min(16u, std::max(1u, hc / 2));
+#undef CU_INIT
+    *out = ctx;
+    return 0;
+}
+
+void b200h_destroy(b200h_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& pr : ctx->prof_events) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    for (DevBuf* b : {&ctx->d_off, &ctx->d_len, &ctx->d_order, &ctx->d_trim, &ctx->d_sha, &ctx->d_md5, &ctx->d_scratch,
+                      &ctx->d_small})
+        if (b->p) cudaFree(b->p);
+    for (int s = 0; s < 2; ++s) {
+        if (ctx->dwave[s]) cudaFree(ctx->dwave[s]);
+        if (ctx->pin[s]) cudaFreeHost(ctx->pin[s]);
+        if (ctx->ev_copied[s]) cudaEventDestroy(ctx->ev_copied[s]);
+        if (ctx->ev_consumed[s]) cudaEventDestroy(ctx->ev_consumed[s]);
+        if (ctx->ev_pin[s]) cudaEventDestroy(ctx->ev_pin[s]);
+    }
+    if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
+    if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    cudaGetLastError();
+    delete ctx;
+}
+
+void* b200h_host_alloc(b200h_ctx* ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    void* p = nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        ctx->err = std::string("cudaHostAlloc failed: ") + cudaGetErrorString(cudaGetLastError());
+        return nullptr;
+    }
+    return p;
+}
+
+void b200h_host_free(b200h_ctx* ctx, void* p) {
+    if (!ctx || !p) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaFreeHost(p);
+    cudaGetLastError();
+}
+
+int b200h_hash_batch_host(b200h_ctx* ctx, const uint8_t* base, const uint64_t* offsets, const uint64_t* lengths,
+                          uint64_t n, uint32_t flags, uint8_t* sha256_out, uint8_t* md5_out,
+                          uint64_t* trimmed_len_out) {
+    if (!ctx) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return hash_batch_host_impl(ctx, base, offsets, lengths, n, flags & 7u, sha256_out, md5_out, trimmed_len_out,
+                                nullptr);
+}
+
+int b200h_hash_batch_device(b200h_ctx* ctx, const void* d_base, const uint64_t* d_offsets, const uint64_t* d_lengths,
+                            uint64_t n, uint32_t flags, void* d_sha256, void* d_md5, uint64_t* d_trimmed_len,
+                            void* cuda_stream) {
+    if (!ctx) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n && (!d_offsets || !d_lengths)) return fail(ctx, B200H_E_INVALID, "offsets/lengths must not be NULL");
+    if (((uintptr_t)d_sha256 | (uintptr_t)d_md5) & 15u)
+        return fail(ctx, B200H_E_INVALID, "digest outputs must be 16-byte aligned");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->s_comp;
+    return enqueue_device_batch(ctx, (const uint8_t*)d_base, d_offsets, d_lengths, n, flags & 7u,
+                                (flags & B200H_SHA256) ? (uint8_t*)d_sha256 : nullptr,
+                                (flags & B200H_MD5) ? (uint8_t*)d_md5 : nullptr, d_trimmed_len, nullptr, st);
+}
+
+int b200h_hash_fixed_parts(b200h_ctx* ctx, const uint8_t* base, uint64_t len, uint64_t part_len, uint32_t flags,
+                           uint8_t* sha256_out, uint8_t* md5_out, uint64_t* trimmed_len_out, uint8_t etag_md5_out[16],
+                           uint64_t* nparts_out) {
+    if (!ctx) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (part_len == 0) return fail(ctx, B200H_E_INVALID, "part_len must be > 0");
+    const uint64_t nparts = (len + part_len - 1) / part_len;
+    if (nparts_out) *nparts_out = nparts;
+    if (nparts == 0) {
+        if (etag_md5_out) {
+            // md5 of the empty concatenation: hash one empty message
+            uint64_t z = 0;
+            return hash_batch_host_impl(ctx, base ? base : (const uint8_t*)&z, &z, &z, 1, B200H_MD5, nullptr,
+                                        etag_md5_out, nullptr, nullptr);
+        }
+        return 0;
+    }
+    std::vector<uint64_t> off(nparts), ln(nparts);
+    for (uint64_t i = 0; i < nparts; ++i) {
+        off[i] = i * part_len;
+        ln[i] = std::min(part_len, len - off[i]);
+    }
+    return hash_batch_host_impl(ctx, base, off.data(), ln.data(), nparts, flags & 7u, sha256_out, md5_out,
+                                trimmed_len_out, etag_md5_out);
+}
+
+// ------------------------------------------------------------------------------------------ streaming
+
+static const uint32_t kShaIv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,
+                                   0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+static const uint32_t kMd5Iv[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+
+static int stream_write_iv(b200h_stream* s) {
+    b200h_ctx* ctx = s->ctx;
+    ChainState init;
+    memcpy(init.sha, kShaIv, sizeof kShaIv);
+    memcpy(init.md5, kMd5Iv, sizeof kMd5Iv);
+    init.prior_bytes = 0;
+    init.reserved = 0;
+    CU_TRY(ctx, cudaMemcpy(s->d_state, &init, sizeof init, cudaMemcpyHostToDevice));
+    s->fill = 0;
+    s->total = 0;
+    return 0;
+}
+
+// absorb the first `nbytes` (multiple of 64) of hbuf into the running state
+static int stream_absorb(b200h_stream* s, size_t nbytes) {
+    b200h_ctx* ctx = s->ctx;
+    if (!nbytes) return 0;
+    const uint64_t meta[2] = {0, nbytes};
+    CU_TRY(ctx, cudaMemcpyAsync(s->d_buf, s->hbuf, nbytes, cudaMemcpyHostToDevice, ctx->s_comp));
+    CU_TRY(ctx, cudaMemcpyAsync(s->d_meta, meta, sizeof meta, cudaMemcpyHostToDevice, ctx->s_comp));
+    if (int rc = enqueue_device_batch(ctx, s->d_buf, s->d_meta, s->d_meta + 1, 1, (s->flags & 3u) | 0x80000000u,
+                                      nullptr, nullptr, nullptr, s->d_state, ctx->s_comp))
+        return rc;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_comp));
+    return 0;
+}
+
+int b200h_stream_new(b200h_ctx* ctx, uint32_t flags, b200h_stream** out) {
+    if (!ctx || !out) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *out = nullptr;
+    if (!(flags & (B200H_SHA256 | B200H_MD5))) return fail(ctx, B200H_E_INVALID, "flags select neither SHA256 nor MD5");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    b200h_stream* s = new (std::nothrow) b200h_stream();
+    if (!s) return fail(ctx, B200H_E_NOMEM, "out of host memory");
+    s->ctx = ctx;
+    s->flags = flags & 3u;
+    s->cap = size_t(1) << 20;
+    s->hbuf = (uint8_t*)malloc(s->cap);
+    uint8_t* blk = nullptr;
+    if (!s->hbuf || cudaMalloc(&blk, s->cap + 2 * sizeof(ChainState) + 64 + 64) != cudaSuccess) {
+        cudaGetLastError();
+        free(s->hbuf);
+        delete s;
+        return fail(ctx, B200H_E_NOMEM, "stream allocation failed");
+    }
+    s->d_state = (ChainState*)blk;
+    s->d_meta = (uint64_t*)(blk + 2 * sizeof(ChainState));
+    s->d_out = blk + 2 * sizeof(ChainState) + 64;
+    s->d_buf = blk + 2 * sizeof(ChainState) + 128;
+    int rc = stream_write_iv(s);
+    if (rc) {
+        cudaFree(blk);
+        free(s->hbuf);
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+int b200h_stream_update(b200h_stream* s, const uint8_t* data, uint64_t len) {
+    if (!s) return B200H_E_INVALID;
+    b200h_ctx* ctx = s->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (len && !data) return fail(ctx, B200H_E_INVALID, "data is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    s->total += len;
+    while (len) {
+        const size_t take = (size_t)std::min<uint64_t>(len, s->cap - s->fill);
+        memcpy(s->hbuf + s->fill, data, take);
+        s->fill += take;
+        data += take;
+        len -= take;
+        if (s->fill == s->cap) {
+            if (int rc = stream_absorb(s, s->cap)) return rc;
+            s->fill = 0;
+        }
+    }
+    return 0;
+}
+
+int b200h_stream_digest(b200h_stream* s, uint8_t sha256_out[32], uint8_t md5_out[16]) {
+    if (!s) return B200H_E_INVALID;
+    b200h_ctx* ctx = s->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    // finalise on a scratch copy of the state so that further updates remain possible
+    const uint64_t meta[2] = {0, s->fill};
+    CU_TRY(ctx, cudaMemcpyAsync(s->d_state + 1, s->d_state, sizeof(ChainState), cudaMemcpyDeviceToDevice, ctx->s_comp));
+    if (s->fill) CU_TRY(ctx, cudaMemcpyAsync(s->d_buf, s->hbuf, s->fill, cudaMemcpyHostToDevice, ctx->s_comp));
+    CU_TRY(ctx, cudaMemcpyAsync(s->d_meta, meta, sizeof meta, cudaMemcpyHostToDevice, ctx->s_comp));
+    if (int rc = enqueue_device_batch(ctx, s->d_buf, s->d_meta, s->d_meta + 1, 1, s->flags, s->d_out, s->d_out + 32,
+                                      nullptr, s->d_state + 1, ctx->s_comp))
+        return rc;
+    uint8_t host[48];
+    CU_TRY(ctx, cudaMemcpyAsync(host, s->d_out, 48, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_comp));
+    if (sha256_out && (s->flags & B200H_SHA256)) memcpy(sha256_out, host, 32);
+    if (md5_out && (s->flags & B200H_MD5)) memcpy(md5_out, host + 32, 16);
+    return 0;
+}
+
+int b200h_stream_reset(b200h_stream* s) {
+    if (!s) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    CU_TRY(s->ctx, cudaSetDevice(s->ctx->device));
+    return stream_write_iv(s);
+}
+
+void b200h_stream_free(b200h_stream* s) {
+    if (!s) return;
+    {
+        std::lock_guard<std::mutex> lk(s->ctx->mu);
+        cudaSetDevice(s->ctx->device);
+        cudaStreamSynchronize(s->ctx->s_comp);
+        cudaFree(s->d_state);
+        cudaGetLastError();
+    }
+    free(s->hbuf);
+    delete s;
+}
+
+// ------------------------------------------------------------------------------------------ utilities
+
+int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64_t seed, uint64_t start,
+                            void* cuda_stream) {
+    if (!ctx) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (((uintptr_t)d_dst & 7u) || (start & 7u)) return fail(ctx, B200H_E_INVALID, "dst/start must be 8-byte aligned");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->s_comp;
+    ctx->launches += launch_fill_synth((uint8_t*)d_dst, nbytes, seed, start, st);
+    CU_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+uint64_t b200h_launch_count(b200h_ctx* ctx) {
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->launches;
+}
+
+int b200h_profile_enable(b200h_ctx* ctx, int on) {
+    if (!ctx) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+int b200h_profile_read(b200h_ctx* ctx, double* ms, uint64_t* launches) {
+    if (!ctx) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    for (auto& pr : ctx->prof_events) {
+        CU_TRY(ctx, cudaEventSynchronize(pr.second));
+        float t = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&t, pr.first, pr.second));
+        ctx->prof_ms += t;
+        ctx->prof_n += 1;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    ctx->prof_events.clear();
+    if (ms) *ms = ctx->prof_ms;
+    if (launches) *launches = ctx->prof_n;
+    ctx->prof_ms = 0.0;
+    ctx->prof_n = 0;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,593 @@
+// b200hash_kernels.cu -- hand-written sm_100a kernels for the blob-ingest / content-hash path.
+//
+// Replaces the hashlib calls of the reference (py/modal/_utils/hash_utils.py:14-101,
+// blob_utils.py:640-705 and :216-219, bytes_io_segment_payload.py:58,102) with batched device
+// kernels.  See DESIGN.md for the data layout and the roofline of each kernel.
+//
+//   lane_hash_kernel   one message per lane; fused SHA-256 + MD5 over a single read of the bytes.
+//                      Each lane pulls its own message through shared memory with 1-D TMA bulk
+//                      copies (cp.async.bulk -> UBLKCP) tracked by a per-warp mbarrier ring, reads
+//                      its slot back with conflict-free 128-bit LDS and runs both compression
+//                      functions interleaved in registers.  Bound: INT32 issue (alu+fma pipes).
+//   trim_kernel        warp per message reverse scan for the last non-zero byte (HBM bound).
+//   plan kernels       bucket messages by block count (longest first) so lanes of a warp run
+//                      the same trip count.
+//   fill_synth_kernel  counter-based synthetic bytes (bench/test data; same stream as synth.py).
+#include "b200hash_kernels.cuh"
+
+namespace b200h {
+
+// ---------------------------------------------------------------------------------- PTX helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+template <int IMM>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(IMM));
+    return d;
+}
+__device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ uint32_t rotl(uint32_t x, int n) { return __funnelshift_l(x, x, n); }
+__device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// ---------------------------------------------------------------------- compression functions
+// SHA-256: FIPS 180-4 section 6.2.2; MD5: RFC 1321 section 3.4.  Boolean functions are single LOP3s:
+//   Ch(e,f,g)=e?f:g (0xCA)  Maj (0xE8)  xor3 (0x96)  MD5 F=b?c:d (0xCA)  G=d?b:c (0xE4)  I=c^(b|~d) (0x39)
+
+#define SHA_S0(x) lop3<0x96>(rotr(x, 2), rotr(x, 13), rotr(x, 22))
+#define SHA_S1(x) lop3<0x96>(rotr(x, 6), rotr(x, 11), rotr(x, 25))
+#define SHA_s0(x) lop3<0x96>(rotr(x, 7), rotr(x, 18), (x) >> 3)
+#define SHA_s1(x) lop3<0x96>(rotr(x, 17), rotr(x, 19), (x) >> 10)
+
+// one SHA round on rotating register names; KW = K[i] + W[i]
+#define SHA_RND(a, b, c, d, e, f, g, h, KW)                        \
+    {                                                              \
+        uint32_t t1 = h + SHA_S1(e) + lop3<0xCA>(e, f, g) + (KW);  \
+        uint32_t t2 = SHA_S0(a) + lop3<0xE8>(a, b, c);             \
+        d += t1;                                                   \
+        h = t1 + t2;                                               \
+    }
+// message schedule in place: w[i&15] becomes W[i] for i >= 16
+#define SHA_SCHED(w, i) \
+    (w[(i)&15] += SHA_s1(w[((i)-2) & 15]) + w[((i)-7) & 15] + SHA_s0(w[((i)-15) & 15]))
+
+#define MD5_STEP(FN, a, b, c, d, xk, s, T)             \
+    {                                                  \
+        a = b + rotl(a + FN(b, c, d) + (xk) + (T), s); \
+    }
+#define MD5_F(b, c, d) lop3<0xCA>(b, c, d)
+#define MD5_G(b, c, d) lop3<0xE4>(b, c, d)
+#define MD5_H(b, c, d) lop3<0x96>(b, c, d)
+#define MD5_I(b, c, d) lop3<0x39>(b, c, d)
+
+// The two hashes are independent dependency chains over the same 16 words, so their rounds are
+// interleaved at source level (4 SHA rounds : 4 MD5 steps) to give every warp two chains of ILP.
+template <bool DO_SHA, bool DO_MD5>
+__device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], const uint32_t (&x)[16],
+                                         bool is_last, uint32_t bits_lo, uint32_t bits_hi) {
+    uint32_t w[16];
+    uint32_t m14 = x[14], m15 = x[15];
+    if (DO_SHA) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = bswap(x[i]);
+        if (is_last) {
+            w[14] = bits_hi;
+            w[15] = bits_lo;
+        }
+    }
+    if (DO_MD5 && is_last) {
+        m14 = bits_lo;
+        m15 = bits_hi;
+    }
+    uint32_t a = hs[0], b = hs[1], c = hs[2], d = hs[3], e = hs[4], f = hs[5], g = hs[6], h = hs[7];
+    uint32_t A = hm[0], B = hm[1], C = hm[2], D = hm[3];
+
+#define SHA4(i, k0, k1, k2, k3)                                 \
+    if (DO_SHA) {                                               \
+        if ((i) >= 16) {                                        \
+            SHA_SCHED(w, (i));                                  \
+            SHA_SCHED(w, (i) + 1);                              \
+            SHA_SCHED(w, (i) + 2);                              \
+            SHA_SCHED(w, (i) + 3);                              \
+        }                                                       \
+        if (((i)&7) == 0) {                                     \
+            SHA_RND(a, b, c, d, e, f, g, h, k0 + w[(i)&15]);    \
+            SHA_RND(h, a, b, c, d, e, f, g, k1 + w[((i) + 1) & 15]); \
+            SHA_RND(g, h, a, b, c, d, e, f, k2 + w[((i) + 2) & 15]); \
+            SHA_RND(f, g, h, a, b, c, d, e, k3 + w[((i) + 3) & 15]); \
+        } else {                                                \
+            SHA_RND(e, f, g, h, a, b, c, d, k0 + w[(i)&15]);    \
+            SHA_RND(d, e, f, g, h, a, b, c, k1 + w[((i) + 1) & 15]); \
+            SHA_RND(c, d, e, f, g, h, a, b, k2 + w[((i) + 2) & 15]); \
+            SHA_RND(b, c, d, e, f, g, h, a, k3 + w[((i) + 3) & 15]); \
+        }                                                       \
+    }
+#define MD4(FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3) \
+    if (DO_MD5) {                                               \
+        MD5_STEP(FN, A, B, C, D, x0, s0, t0);                   \
+        MD5_STEP(FN, D, A, B, C, x1, s1, t1);                   \
+        MD5_STEP(FN, C, D, A, B, x2, s2, t2);                   \
+        MD5_STEP(FN, B, C, D, A, x3, s3, t3);                   \
+    }
+
+    SHA4(0, 0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u)
+    MD4(MD5_F, x[0], x[1], x[2], x[3], 7, 12, 17, 22, 0xd76aa478u, 0xe8c7b756u, 0x242070dbu, 0xc1bdceeeu)
+    SHA4(4, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u)
+    MD4(MD5_F, x[4], x[5], x[6], x[7], 7, 12, 17, 22, 0xf57c0fafu, 0x4787c62au, 0xa8304613u, 0xfd469501u)
+    SHA4(8, 0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u)
+    MD4(MD5_F, x[8], x[9], x[10], x[11], 7, 12, 17, 22, 0x698098d8u, 0x8b44f7afu, 0xffff5bb1u, 0x895cd7beu)
+    SHA4(12, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u)
+    MD4(MD5_F, x[12], x[13], m14, m15, 7, 12, 17, 22, 0x6b901122u, 0xfd987193u, 0xa679438eu, 0x49b40821u)
+    SHA4(16, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu)
+    MD4(MD5_G, x[1], x[6], x[11], x[0], 5, 9, 14, 20, 0xf61e2562u, 0xc040b340u, 0x265e5a51u, 0xe9b6c7aau)
+    SHA4(20, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau)
+    MD4(MD5_G, x[5], x[10], m15, x[4], 5, 9, 14, 20, 0xd62f105du, 0x02441453u, 0xd8a1e681u, 0xe7d3fbc8u)
+    SHA4(24, 0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u)
+    MD4(MD5_G, x[9], m14, x[3], x[8], 5, 9, 14, 20, 0x21e1cde6u, 0xc33707d6u, 0xf4d50d87u, 0x455a14edu)
+    SHA4(28, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u)
+    MD4(MD5_G, x[13], x[2], x[7], x[12], 5, 9, 14, 20, 0xa9e3e905u, 0xfcefa3f8u, 0x676f02d9u, 0x8d2a4c8au)
+    SHA4(32, 0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u)
+    MD4(MD5_H, x[5], x[8], x[11], m14, 4, 11, 16, 23, 0xfffa3942u, 0x8771f681u, 0x6d9d6122u, 0xfde5380cu)
+    SHA4(36, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u)
+    MD4(MD5_H, x[1], x[4], x[7], x[10], 4, 11, 16, 23, 0xa4beea44u, 0x4bdecfa9u, 0xf6bb4b60u, 0xbebfbc70u)
+    SHA4(40, 0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u)
+    MD4(MD5_H, x[13], x[0], x[3], x[6], 4, 11, 16, 23, 0x289b7ec6u, 0xeaa127fau, 0xd4ef3085u, 0x04881d05u)
+    SHA4(44, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u)
+    MD4(MD5_H, x[9], x[12], m15, x[2], 4, 11, 16, 23, 0xd9d4d039u, 0xe6db99e5u, 0x1fa27cf8u, 0xc4ac5665u)
+    SHA4(48, 0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u)
+    MD4(MD5_I, x[0], x[7], m14, x[5], 6, 10, 15, 21, 0xf4292244u, 0x432aff97u, 0xab9423a7u, 0xfc93a039u)
+    SHA4(52, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u)
+    MD4(MD5_I, x[12], x[3], x[10], x[1], 6, 10, 15, 21, 0x655b59c3u, 0x8f0ccc92u, 0xffeff47du, 0x85845dd1u)
+    SHA4(56, 0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u)
+    MD4(MD5_I, x[8], m15, x[6], x[13], 6, 10, 15, 21, 0x6fa87e4fu, 0xfe2ce6e0u, 0xa3014314u, 0x4e0811a1u)
+    SHA4(60, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u)
+    MD4(MD5_I, x[4], x[11], x[2], x[9], 6, 10, 15, 21, 0xf7537e82u, 0xbd3af235u, 0x2ad7d2bbu, 0xeb86d391u)
+#undef SHA4
+#undef MD4
+
+    if (DO_SHA) {
+        hs[0] += a; hs[1] += b; hs[2] += c; hs[3] += d;
+        hs[4] += e; hs[5] += f; hs[6] += g; hs[7] += h;
+    }
+    if (DO_MD5) {
+        hm[0] += A; hm[1] += B; hm[2] += C; hm[3] += D;
+    }
+}
+
+// ------------------------------------------------------------------------------ lane_hash_kernel
+
+constexpr int kLaneThreads = 128;  // 4 warps; every warp runs an independent TMA/mbarrier ring
+constexpr int kLaneWarps = kLaneThreads / 32;
+constexpr int kBPC = 2;     // 64-byte blocks per chunk (one bulk copy)
+constexpr int kStages = 2;  // chunks in flight per lane
+constexpr int kSlot = kBPC * 64 + 16;  // +16: holds the misaligned-start granule and de-conflicts LDS.128
+constexpr int kWarpSmem = kStages * 32 * kSlot;
+constexpr int kLaneSmem = kLaneWarps * kWarpSmem + kLaneWarps * kStages * 8;
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        uint64_t t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+template <bool DO_SHA, bool DO_MD5>
+__global__ void __launch_bounds__(kLaneThreads, 5)
+lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
+                 const uint32_t* __restrict__ order, uint64_t n, uint32_t flags, int lanes_per_warp,
+                 uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out, ChainState* __restrict__ state) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    uint8_t* ring = smem + wib * kWarpSmem;
+    const uint32_t bar0 = smem_u32(smem + kLaneWarps * kWarpSmem) + wib * kStages * 8;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncwarp();
+
+    // ---- which message does this lane own
+    const uint64_t wglobal = (uint64_t)blockIdx.x * kLaneWarps + wib;
+    const uint64_t slot_idx = wglobal * (uint64_t)lanes_per_warp + lane;
+    const bool active = lane < lanes_per_warp && slot_idx < n;
+    const uint32_t mi = active ? (order ? order[slot_idx] : (uint32_t)slot_idx) : 0u;
+    const bool final = !(flags & F_NO_FINAL);
+
+    const uint8_t* p = base;
+    uint64_t L = 0;
+    if (active) {
+        p = base + off[mi];
+        L = len[mi];
+    }
+    uint32_t hs[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,
+                      0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    uint32_t hm[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+    uint64_t prior = 0;
+    if (state && active) {
+        const uint4* sp = reinterpret_cast<const uint4*>(&state[mi]);
+        uint4 q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3];
+        hs[0] = q0.x; hs[1] = q0.y; hs[2] = q0.z; hs[3] = q0.w;
+        hs[4] = q1.x; hs[5] = q1.y; hs[6] = q1.z; hs[7] = q1.w;
+        hm[0] = q2.x; hm[1] = q2.y; hm[2] = q2.z; hm[3] = q2.w;
+        prior = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
+    }
+    const uint64_t nfull = L >> 6;                      // blocks that stream through shared memory
+    const uint32_t r = final ? (uint32_t)(L & 63) : 0;  // bytes of the padded tail block
+    const uint32_t ntail = !active ? 0u : (final ? (r < 56 ? 1u : 2u) : 0u);
+    const uint64_t nsteps = nfull + ntail;
+    const uint64_t bits = (prior + L) << 3;
+    const uint32_t bits_lo = (uint32_t)bits, bits_hi = (uint32_t)(bits >> 32);
+
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);  // misalignment of the message start
+    const uint8_t* p0 = p - mis;                                            // 16B-aligned copy source
+    const bool warp_aligned = __all_sync(0xffffffffu, mis == 0);
+    const uint64_t nchunks = (nfull + kBPC - 1) / kBPC;
+    const uint64_t max_chunks = warp_max_u64(nchunks);
+    const uint64_t max_outer = (warp_max_u64(nsteps) + kBPC - 1) / kBPC;
+
+    auto issue = [&](uint64_t c) {
+        const uint32_t st = (uint32_t)(c % kStages);
+        uint32_t bytes = 0;
+        if (c < nchunks) {
+            const uint64_t rem = nfull - c * kBPC;
+            bytes = (rem < kBPC ? (uint32_t)rem : (uint32_t)kBPC) * 64u + (mis ? 16u : 0u);
+        }
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        if (total == 0) return;
+        if (lane == 0) mbar_arrive_expect_tx(bar0 + 8 * st, total);
+        __syncwarp();
+        if (bytes) bulk_g2s(smem_u32(ring + (st * 32 + lane) * kSlot), p0 + c * (kBPC * 64), bytes, bar0 + 8 * st);
+    };
+
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) issue(s);
+
+    for (uint64_t c = 0; c < max_outer; ++c) {
+        const uint32_t st = (uint32_t)(c % kStages);
+        if (c < max_chunks) mbar_wait(bar0 + 8 * st, (uint32_t)((c / kStages) & 1));
+        const uint8_t* slot = ring + (st * 32 + lane) * kSlot;
+#pragma unroll 1
+        for (int j = 0; j < kBPC; ++j) {
+            const uint64_t step = c * kBPC + j;
+            if (step < nsteps) {
+                uint32_t x[16];
+                if (step < nfull) {
+                    const uint8_t* blk = slot + j * 64;
+                    if (warp_aligned) {
+                        const uint4* q = reinterpret_cast<const uint4*>(blk);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint4 v = q[k];
+                            x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+                        }
+                    } else {
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(blk + (mis & ~3u));
+                        const uint32_t sh = (mis & 3u) * 8u;
+                        uint32_t y[17];
+#pragma unroll
+                        for (int k = 0; k < 17; ++k) y[k] = wp[k];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) x[k] = __funnelshift_r(y[k], y[k + 1], sh);
+                    }
+                } else if (step == nfull) {
+                    // first tail block: the r leftover bytes straight from global (aligned 32-bit words,
+                    // only words that contain a message byte), then 0x80 and zero fill.
+                    const uint8_t* g = p + (nfull << 6);
+                    const uint32_t gm = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u);
+                    const uint32_t* gw = reinterpret_cast<const uint32_t*>(g - gm);
+                    const uint32_t span = r ? gm + r : 0u;  // bytes from gw to the end of the message
+                    uint32_t y[17];
+#pragma unroll
+                    for (int k = 0; k < 17; ++k) y[k] = (4u * k < span) ? __ldg(gw + k) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        uint32_t v = __funnelshift_r(y[k], y[k + 1], gm * 8u);
+                        const int have = (int)r - 4 * k;  // message bytes in this word
+                        if (have <= 0) v = 0;
+                        else if (have < 4) v &= (1u << (8 * have)) - 1u;
+                        if (have >= 0 && have < 4) v |= 0x80u << (8 * have);
+                        x[k] = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) x[k] = 0u;
+                }
+                const bool is_last = final && (step + 1 == nsteps);
+                compress<DO_SHA, DO_MD5>(hs, hm, x, is_last, bits_lo, bits_hi);
+            }
+        }
+        // the slot is private to this lane; order its generic-proxy reads before the async refill
+        fence_proxy_async();
+        __syncwarp();
+        if (c + kStages < max_chunks) issue(c + kStages);
+    }
+
+    if (!active) return;
+    if (final) {
+        if (DO_SHA && sha_out) {
+            uint4* o = reinterpret_cast<uint4*>(sha_out + 32ull * mi);
+            o[0] = make_uint4(bswap(hs[0]), bswap(hs[1]), bswap(hs[2]), bswap(hs[3]));
+            o[1] = make_uint4(bswap(hs[4]), bswap(hs[5]), bswap(hs[6]), bswap(hs[7]));
+        }
+        if (DO_MD5 && md5_out) {
+            *reinterpret_cast<uint4*>(md5_out + 16ull * mi) = make_uint4(hm[0], hm[1], hm[2], hm[3]);
+        }
+    }
+    if (state && !final) {
+        uint4* sp = reinterpret_cast<uint4*>(&state[mi]);
+        const uint64_t np = prior + L;
+        sp[0] = make_uint4(hs[0], hs[1], hs[2], hs[3]);
+        sp[1] = make_uint4(hs[4], hs[5], hs[6], hs[7]);
+        sp[2] = make_uint4(hm[0], hm[1], hm[2], hm[3]);
+        sp[3] = make_uint4((uint32_t)np, (uint32_t)(np >> 32), 0u, 0u);
+    }
+}
+
+// ------------------------------------------------------------------------------------ trim_kernel
+// Reference semantics (blob_utils.py:667-705): index just past the last non-zero byte, 0 when the
+// message is empty or all zero.  One warp per message scanning backwards, 4 x 16 B per lane in flight.
+
+__global__ void __launch_bounds__(256)
+trim_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
+            uint64_t n, uint64_t* __restrict__ trimmed) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t m = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); m < n; m += warps) {
+        const uint8_t* p = base + off[m];
+        uint64_t end = len[m];
+        uint64_t found = 0;  // 1 + index of last non-zero byte
+        // unaligned tail bytes first so the bulk of the scan runs on 16B-aligned granules
+        const uint64_t a_end = (reinterpret_cast<uintptr_t>(p) + end) & 15u;  // bytes past the last aligned boundary
+        uint64_t tail = a_end < end ? a_end : end;
+        {
+            uint32_t hit = 0;
+            if ((uint64_t)lane < tail && p[end - 1 - lane] != 0) hit = 1;  // lane 0 = last byte
+            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            if (mask) found = end - (uint64_t)(__ffs(mask) - 1);
+            end -= tail;
+        }
+        while (!found && end >= 16) {
+            // granules [end-16*(k+1), end-16*k) for k = lane + 32*u, u = 0..3 (nearest the end first)
+            uint4 v[4];
+            uint64_t pos[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t k = (uint64_t)lane + 32u * u;
+                const bool ok = 16 * (k + 1) <= end;  // p + end is 16B-aligned here
+                pos[u] = ok ? end - 16 * (k + 1) : ~0ull;
+                v[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(p + pos[u])) : make_uint4(0, 0, 0, 0);
+            }
+            uint64_t best = 0;
+#pragma unroll
+            for (int u = 3; u >= 0; --u) {
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (w[q]) {
+                        const uint64_t cand = pos[u] + 4 * q + (4 - (__clz(w[q]) >> 3));
+                        best = cand > best ? cand : best;
+                    }
+            }
+            best = warp_max_u64(best);
+            if (best) found = best;
+            const uint64_t whole = end & ~15ull;
+            end -= whole < 2048 ? whole : 2048;
+        }
+        if (!found && end > 0 && end < 16) {
+            // fewer than 16 bytes remain at the (unaligned) head of the message
+            uint32_t hit = 0;
+            if ((uint64_t)lane < end && p[end - 1 - lane] != 0) hit = 1;
+            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            if (mask) found = end - (uint64_t)(__ffs(mask) - 1);
+        }
+        if (lane == 0) trimmed[m] = found;
+    }
+}
+
+// ------------------------------------------------------------------------------------ plan kernels
+// Bucket key: exact block count below 16, then 8 sub-buckets per power of two (<= 12.5 % spread inside
+// a bucket, so lanes of a warp run nearly equal trip counts).  Buckets are laid out longest first.
+
+__device__ __forceinline__ uint32_t plan_bucket(uint64_t len) {
+    const uint64_t nb = (len >> 6) + 1;
+    if (nb < 16) return (uint32_t)nb;
+    const int e = 63 - __clzll((long long)nb);
+    const uint32_t b = 16u + (uint32_t)(e - 4) * 8u + (uint32_t)((nb >> (e - 3)) & 7u);
+    return b < (uint32_t)kPlanBuckets ? b : (uint32_t)kPlanBuckets - 1;
+}
+
+__global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[kPlanBuckets];
+    for (int i = threadIdx.x; i < kPlanBuckets; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[plan_bucket(len[i])], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kPlanBuckets; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// hist[0..B) counts -> cursor[0..B) start positions, longest bucket first.  Single CTA of kPlanBuckets threads.
+__global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t sh[kPlanBuckets];
+    const int t = threadIdx.x;
+    const int rev = kPlanBuckets - 1 - t;  // position in longest-first order
+    sh[t] = hist[rev];
+    __syncthreads();
+    for (int o = 1; o < kPlanBuckets; o <<= 1) {
+        uint32_t v = t >= o ? sh[t - o] : 0u;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    cursor[rev] = sh[t] - hist[rev];  // exclusive
+}
+
+__global__ void plan_scatter_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ cursor,
+                                    uint32_t* __restrict__ order) {
+    // warp-aggregated atomics: lanes hitting the same bucket share one atomicAdd
+    for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < n;
+         i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + (threadIdx.x & 31);
+        const bool ok = i < n;
+        const uint32_t b = ok ? plan_bucket(len[i]) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(peers) - 1;
+        uint32_t basepos = 0;
+        if (ok && (threadIdx.x & 31) == leader) basepos = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (ok) order[basepos + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u))] = (uint32_t)i;
+    }
+}
+
+// ------------------------------------------------------------------------------- utility kernels
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// dst[0..nbytes) = bytes [start, start+nbytes) of synthetic stream `seed` (see modal_client_b200/synth.py).
+// dst must be 8-byte aligned and start a multiple of 8; the last partial word is written bytewise.
+__global__ void fill_synth_kernel(uint8_t* __restrict__ dst, uint64_t nbytes, uint64_t seed_mul, uint64_t word0) {
+    const uint64_t nwords = nbytes >> 3;
+    uint64_t* d64 = reinterpret_cast<uint64_t*>(dst);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nwords;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = mix64(seed_mul + word0 + i);
+        if (i < nwords) {
+            d64[i] = v;
+        } else {
+            for (uint64_t b = 0; b < (nbytes & 7); ++b) dst[8 * nwords + b] = (uint8_t)(v >> (8 * b));
+        }
+    }
+}
+
+// off[i] = i*part_len, len[i] = min(part_len, total - off[i])  (multipart parts / 8 MiB blocks of one buffer)
+__global__ void iota_parts_kernel(uint64_t* off, uint64_t* len, uint64_t total, uint64_t part_len, uint64_t nparts) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nparts;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = i * part_len;
+        off[i] = o;
+        len[i] = total - o < part_len ? total - o : part_len;
+    }
+}
+
+// --------------------------------------------------------------------------------- launch wrappers
+
+static int grid_for(uint64_t n, int threads, int cap) {
+    uint64_t g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    return (int)(g > (uint64_t)cap ? (uint64_t)cap : g);
+}
+
+int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n, uint64_t* trimmed,
+                cudaStream_t st) {
+    if (!n) return 0;
+    trim_kernel<<<grid_for(n * 32, 256, 148 * 8), 256, 0, st>>>(base, off, len, n, trimmed);
+    return 1;
+}
+
+int launch_plan(const uint64_t* len, uint64_t n, uint32_t* order, uint32_t* scratch, cudaStream_t st) {
+    if (!n) return 0;
+    uint32_t* hist = scratch;
+    uint32_t* cursor = scratch + kPlanBuckets;
+    cudaMemsetAsync(hist, 0, sizeof(uint32_t) * kPlanBuckets, st);
+    plan_hist_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, hist);
+    plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor);
+    plan_scatter_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, cursor, order);
+    return 3;
+}
+
+template <bool S, bool M>
+static void launch_lane_t(int grid, const uint8_t* base, const uint64_t* off, const uint64_t* len,
+                          const uint32_t* order, uint64_t n, uint32_t flags, int lpw, uint8_t* sha_out,
+                          uint8_t* md5_out, ChainState* state, cudaStream_t st) {
+    lane_hash_kernel<S, M><<<grid, kLaneThreads, kLaneSmem, st>>>(base, off, len, order, n, flags, lpw, sha_out,
+                                                                md5_out, state);
+}
+
+int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* order,
+                     uint64_t n, uint32_t flags, int lpw, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
+                     cudaStream_t st) {
+    if (!n) return 0;
+    if (lpw < 1) lpw = 1;
+    if (lpw > 32) lpw = 32;
+    const uint64_t warps = (n + lpw - 1) / lpw;
+    const uint64_t grid = (warps + kLaneWarps - 1) / kLaneWarps;
+    const bool s = flags & F_SHA256, m = flags & F_MD5;
+    if (s && m) launch_lane_t<true, true>((int)grid, base, off, len, order, n, flags, lpw, sha_out, md5_out, state, st);
+    else if (s) launch_lane_t<true, false>((int)grid, base, off, len, order, n, flags, lpw, sha_out, md5_out, state, st);
+    else if (m) launch_lane_t<false, true>((int)grid, base, off, len, order, n, flags, lpw, sha_out, md5_out, state, st);
+    else return 0;
+    return 1;
+}
+
+int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t start, cudaStream_t st) {
+    if (!nbytes) return 0;
+    fill_synth_kernel<<<grid_for((nbytes >> 3) + 1, 256, 148 * 16), 256, 0, st>>>(dst, nbytes, seed * 0xD1342543DE82EF95ull,
+                                                                                 start >> 3);
+    return 1;
+}
+
+int launch_iota_parts(uint64_t* off, uint64_t* len, uint64_t total, uint64_t part_len, uint64_t nparts,
+                      cudaStream_t st) {
+    if (!nparts) return 0;
+    iota_parts_kernel<<<grid_for(nparts, 256, 148 * 4), 256, 0, st>>>(off, len, total, part_len, nparts);
+    return 1;
+}
+
+cudaError_t configure_kernels() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(lane_hash_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lane_hash_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lane_hash_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
+    return e;
+}
+
+const char* kernel_build_info() {
+    return "b200hash kernels: sm_100a, lane_hash(threads=128, blocks/chunk=2, stages=2, slot=144B), " __DATE__;
+}
+
+}  // namespace b200h

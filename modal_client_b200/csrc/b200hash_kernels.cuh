@@ -1,0 +1,41 @@
+// b200hash_kernels.cuh -- device-side declarations shared by the kernel and host translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200h {
+
+// Per-message chaining state for streamed / segmented messages (64 B, 16-byte aligned).
+struct alignas(16) ChainState {
+    uint32_t sha[8];
+    uint32_t md5[4];
+    uint64_t prior_bytes;  // bytes already absorbed before this segment
+    uint64_t reserved;
+};
+
+enum : uint32_t {
+    F_SHA256 = 1u,
+    F_MD5 = 2u,
+    F_TRIM = 4u,      // hash the zero-trimmed prefix of every message, report trimmed length
+    F_NO_FINAL = 8u,  // continuation segment: len % 64 == 0, no padding, write ChainState back
+};
+
+constexpr int kPlanBuckets = 512;
+
+// Launch wrappers (defined in b200hash_kernels.cu).  All asynchronous on `st`.
+// Every wrapper returns the number of kernels it launched (for gpu_launches accounting).
+int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n, uint64_t* trimmed,
+                cudaStream_t st);
+int launch_plan(const uint64_t* len, uint64_t n, uint32_t* order, uint32_t* hist_scratch /*2*kPlanBuckets+2*/,
+                cudaStream_t st);
+int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* order,
+                     uint64_t n, uint32_t flags, int lanes_per_warp, uint8_t* sha_out, uint8_t* md5_out,
+                     ChainState* state, cudaStream_t st);
+int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t start, cudaStream_t st);
+int launch_iota_parts(uint64_t* off, uint64_t* len, uint64_t total, uint64_t part_len, uint64_t nparts,
+                      cudaStream_t st);
+
+cudaError_t configure_kernels();  // one-time cudaFuncSetAttribute calls for the current device
+const char* kernel_build_info();
+
+}  // namespace b200h

@@ -1,0 +1,166 @@
+"""GPU: bit-exact parity of the CUDA path (through the C ABI) against the oracle and golden fixtures."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from modal_client_b200 import _lib
+from modal_client_b200.synth import materialize, synth_array, synth_bytes
+from oracle import c_oracle, ref_port
+
+pytestmark = pytest.mark.gpu
+
+BOTH = _lib.SHA256 | _lib.MD5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _lib.Context(0, pinned_bytes=64 << 20, device_bytes=512 << 20)
+    yield c
+    c.close()
+
+
+def _check(buf, off, ln, sha, md5):
+    s, m, _ = c_oracle.hash_batch(buf, off, ln)
+    assert np.array_equal(sha, s)
+    assert np.array_equal(md5, m)
+
+
+def test_every_length_0_to_300_unaligned_packed(ctx):
+    lens = np.arange(0, 301, dtype=np.uint64)
+    offs = np.concatenate([[3], 3 + np.cumsum(lens + 1)])[:-1].astype(np.uint64)  # odd, unaligned starts
+    buf = synth_array(11, int(offs[-1] + lens[-1]) + 8)
+    sha, md5, trimmed = ctx.hash_batch_host(buf, offs, lens, BOTH)
+    assert np.array_equal(trimmed, lens)
+    _check(buf, offs, lens, sha, md5)
+    for i in (0, 1, 55, 56, 63, 64, 65, 119, 120, 127, 128, 300):
+        msg = buf[int(offs[i]) : int(offs[i] + lens[i])].tobytes()
+        assert sha[i].tobytes() == hashlib.sha256(msg).digest()
+        assert md5[i].tobytes() == hashlib.md5(msg).digest()
+
+
+def test_aligned_and_mixed_sizes(ctx):
+    rng = np.random.default_rng(5)
+    lens = np.concatenate([rng.integers(0, 70000, 700), [0, 64, 1 << 20, (1 << 20) + 1, 262144, 262144]]).astype(
+        np.uint64
+    )
+    offs = np.zeros_like(lens)
+    pos = 0
+    for i, n in enumerate(lens):
+        offs[i] = pos
+        pos += (int(n) + 15) & ~15
+    buf = synth_array(12, pos + 16)
+    sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, BOTH)
+    _check(buf, offs, lens, sha, md5)
+
+
+def test_single_flags(ctx):
+    buf = synth_array(13, 100000)
+    offs = np.array([0, 1000, 50000], np.uint64)
+    lens = np.array([1000, 49000, 50000], np.uint64)
+    s, m, _ = c_oracle.hash_batch(buf, offs, lens)
+    sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, _lib.SHA256)
+    assert md5 is None and np.array_equal(sha, s)
+    sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, _lib.MD5)
+    assert sha is None and np.array_equal(md5, m)
+
+
+def test_separate_buffers_absolute_addresses(ctx):
+    bufs = [synth_bytes(20 + i, n) for i, n in enumerate([0, 5, 64, 1000, 65536, 300001])]
+    sha, md5, _ = ctx.hash_buffers(bufs)
+    for b, s, m in zip(bufs, sha, md5):
+        assert s.tobytes() == c_oracle.sha256(b) and m.tobytes() == c_oracle.md5(b)
+
+
+def test_golden_hash_utils_vectors(ctx, golden):
+    cases = golden("hash_utils.json")["bytes_cases"]
+    bufs = [materialize(c["input"]) for c in cases]
+    sha, md5, _ = ctx.hash_buffers(bufs)
+    for c, s, m in zip(cases, sha, md5):
+        assert s.tobytes().hex() == c["sha256_hex"]
+        assert m.tobytes().hex() == c["md5_hex"]
+
+
+def test_trim_zeros_blocks_golden(ctx, golden):
+    for c in golden("blocks.json")["spec2"]:
+        data = materialize(c["input"])
+        bs = c["patch"].get("BLOCK_SIZE", 8 << 20)
+        sha, _, trimmed, _ = ctx.hash_fixed_parts(data, bs, _lib.SHA256 | _lib.TRIM_ZEROS)
+        got = [[i * bs, i * bs + int(t), s.tobytes().hex()] for i, (t, s) in enumerate(zip(trimmed, sha))]
+        assert got == c["blocks"]
+
+
+def test_trim_random_zero_runs(ctx):
+    rng = np.random.default_rng(9)
+    lens = rng.integers(0, 9000, 300).astype(np.uint64)
+    gaps = rng.integers(0, 40, 300).astype(np.uint64)
+    offs = (np.concatenate([[0], np.cumsum(lens + gaps)])[:-1] + 5).astype(np.uint64)
+    buf = synth_array(14, int(offs[-1] + lens[-1]) + 64).copy()
+    for i in range(0, 300, 2):
+        z = min(int(lens[i]), int(rng.integers(0, 6000)))
+        buf[int(offs[i] + lens[i]) - z : int(offs[i] + lens[i])] = 0
+    sha, md5, trimmed = ctx.hash_batch_host(buf, offs, lens, BOTH | _lib.TRIM_ZEROS)
+    s, m, e = c_oracle.hash_batch(buf, offs, lens, trim=True)
+    assert np.array_equal(trimmed, e) and np.array_equal(sha, s) and np.array_equal(md5, m)
+
+
+def test_multipart_golden(ctx, golden):
+    for c in golden("multipart.json")["cases"]:
+        data = materialize(c["input"])
+        _, md5, _, etag = ctx.hash_fixed_parts(data, c["part_len"], _lib.MD5, want_etag=True)
+        assert [m.tobytes().hex() for m in md5] == c["part_md5_hex"]
+        assert f"{etag.hex()}-{len(md5)}" == c["etag"]
+
+
+def test_stream_matches_one_shot(ctx):
+    data = synth_bytes(15, 3 * (1 << 20) + 777)
+    st = ctx.stream(BOTH)
+    pos = 0
+    for step in [1, 63, 64, 65, 4096, 65536, 1 << 20, 1 << 21]:
+        st.update(data[pos : pos + step])
+        pos += step
+        s, m = st.digests()  # non-destructive
+        assert s == hashlib.sha256(data[:pos]).digest() and m == hashlib.md5(data[:pos]).digest()
+    st.update(data[pos:])
+    s, m = st.digests()
+    assert s == c_oracle.sha256(data) and m == c_oracle.md5(data)
+    st.reset()
+    st.update(b"abc")
+    assert st.digests()[0].hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    st.close()
+
+
+def test_device_resident_batch_matches_host_and_oracle(ctx):
+    import torch
+
+    n, size = 3000, 262144
+    dev = torch.device("cuda:0")
+    data = torch.empty(n * size, dtype=torch.uint8, device=dev)
+    ctx.fill_synth_device(data.data_ptr(), n * size, seed=77)
+    torch.cuda.synchronize()
+    # the device generator and the numpy generator are the same stream
+    assert np.array_equal(data[: 1 << 16].cpu().numpy(), synth_array(77, 1 << 16))
+    off = torch.arange(n, dtype=torch.int64, device=dev) * size
+    ln = torch.full((n,), size, dtype=torch.int64, device=dev)
+    sha = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    md5 = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.hash_batch_device(data.data_ptr(), off.data_ptr(), ln.data_ptr(), n, BOTH, sha.data_ptr(), md5.data_ptr(), 0, st)
+    torch.cuda.synchronize()
+    sha_h, md5_h = sha.cpu().numpy(), md5.cpu().numpy()
+    for i in (0, 1, 31, 32, 1499, n - 1):
+        msg = synth_bytes(77, size, start=i * size)
+        up = ref_port.upload_hashes(msg)
+        assert sha_h[i].tobytes().hex() == up.sha256_hex() and md5_h[i].tobytes().hex() == up.md5_hex()
+    # size-independent property: the host path over the same bytes gives the same digest table
+    host = data.cpu().numpy()
+    sha2, md52, _ = ctx.hash_batch_host(host, off.cpu().numpy(), ln.cpu().numpy(), BOTH)
+    assert np.array_equal(sha2, sha_h) and np.array_equal(md52, md5_h)
+
+
+def test_one_large_message_and_64bit_lengths(ctx):
+    n = (1 << 27) + 12345  # 128 MiB: crosses wave / pinned-slot boundaries
+    data = synth_array(16, n)
+    sha, md5, _ = ctx.hash_batch_host(data, [0], [n], BOTH)
+    assert sha[0].tobytes() == hashlib.sha256(data).digest()
+    assert md5[0].tobytes() == hashlib.md5(data).digest()
