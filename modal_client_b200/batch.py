@@ -1,0 +1,73 @@
+"""Batch front door of the B200 hash path: many independent messages in, one digest table out.
+
+This is the call the accelerated callers make (map input pump, Volume.batch_upload v1/v2, multipart
+parts): the reference hashes one payload / file / block at a time with hashlib
+(py/modal/_utils/blob_utils.py:345,459-474,640-664); here the whole set goes to the GPU in one call.
+"""
+from __future__ import annotations
+
+import base64
+import dataclasses
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import MD5, SHA256, TRIM_ZEROS, Context, default_context
+
+
+@dataclasses.dataclass
+class DigestTable:
+    """Fixed-width digest table, row i = message i.  ``sha256``: uint8[n,32] or None; ``md5``:
+    uint8[n,16] or None; ``hashed_len``: uint64[n] bytes actually hashed (differs from the input
+    length only with zero trimming)."""
+
+    sha256: np.ndarray | None
+    md5: np.ndarray | None
+    hashed_len: np.ndarray
+
+    def __len__(self) -> int:
+        return int(self.hashed_len.size)
+
+    def sha256_hex(self, i: int) -> str:
+        return self.sha256[i].tobytes().hex()
+
+    def md5_hex(self, i: int) -> str:
+        return self.md5[i].tobytes().hex()
+
+    def sha256_base64(self, i: int) -> str:
+        return base64.b64encode(self.sha256[i].tobytes()).decode("ascii")
+
+    def md5_base64(self, i: int) -> str:
+        return base64.b64encode(self.md5[i].tobytes()).decode("ascii")
+
+    def packed(self) -> np.ndarray:
+        """uint8[n,48]: sha256 || md5 per row -- the table the ranks all-gather."""
+        n = len(self)
+        out = np.zeros((n, 48), np.uint8)
+        if self.sha256 is not None:
+            out[:, :32] = self.sha256
+        if self.md5 is not None:
+            out[:, 32:] = self.md5
+        return out
+
+
+def hash_table_host(base, offsets, lengths, *, sha256: bool = True, md5: bool = True, trim_zeros: bool = False,
+                    ctx: Context | None = None) -> DigestTable:
+    """Hash messages ``base[offsets[i] : offsets[i]+lengths[i]]`` that live in host memory
+    (page-locked memory from ``Context.host_alloc`` is DMA'd directly; anything else is staged)."""
+    ctx = ctx or default_context()
+    flags = (SHA256 if sha256 else 0) | (MD5 if md5 else 0) | (TRIM_ZEROS if trim_zeros else 0)
+    s, m, t = ctx.hash_batch_host(base, offsets, lengths, flags)
+    return DigestTable(s, m, t)
+
+
+def hash_table_buffers(bufs: Sequence, *, sha256: bool = True, md5: bool = True, ctx: Context | None = None) -> DigestTable:
+    """Hash many separate bytes-like objects (e.g. serialized map inputs) in one GPU batch."""
+    ctx = ctx or default_context()
+    flags = (SHA256 if sha256 else 0) | (MD5 if md5 else 0)
+    s, m, t = ctx.hash_buffers(bufs, flags)
+    return DigestTable(s, m, t)
+
+
+__all__ = ["DigestTable", "hash_table_host", "hash_table_buffers", "Context", "default_context", "_lib"]
