@@ -161,7 +161,8 @@ def run_gpu(args) -> None:
     if world > 1:
         sha_all = torch.empty((world * N_MSG, 32), dtype=torch.uint8, device=dev)
         md5_all = torch.empty((world * N_MSG, 16), dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # non-default stream: the library launches on this very handle
+    torch.cuda.set_stream(stream)
     torch.cuda.synchronize()
 
     def step():

@@ -15,7 +15,7 @@ from typing import Sequence
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libb200hash.so")
+LIB_PATH = os.environ.get("B200H_LIB") or os.path.join(_PKG, "libb200hash.so")  # override: experiments only
 CSRC = os.path.join(_PKG, "csrc")
 
 SHA256 = 1

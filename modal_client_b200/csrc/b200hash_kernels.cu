@@ -57,6 +57,13 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(IMM));
     return d;
 }
+// a + b issued as IMAD (a * one + b) so that the add runs on the FMA pipe instead of the ALU pipe, which
+// SHF/LOP3/PRMT already saturate.  `one` is a kernel argument (== 1) so ptxas cannot fold the multiply.
+__device__ __forceinline__ uint32_t addf(uint32_t a, uint32_t b, uint32_t one) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 __device__ __forceinline__ uint32_t rotl(uint32_t x, int n) { return __funnelshift_l(x, x, n); }
 __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
@@ -71,20 +78,40 @@ __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0,
 #define SHA_s1(x) lop3<0x96>(rotr(x, 17), rotr(x, 19), (x) >> 10)
 
 // one SHA round on rotating register names; KW = K[i] + W[i]
-#define SHA_RND(a, b, c, d, e, f, g, h, KW)                        \
-    {                                                              \
-        uint32_t t1 = h + SHA_S1(e) + lop3<0xCA>(e, f, g) + (KW);  \
-        uint32_t t2 = SHA_S0(a) + lop3<0xE8>(a, b, c);             \
-        d += t1;                                                   \
-        h = t1 + t2;                                               \
+// B200H_ADDMODE selects where the additions run: 0 = plain C (ptxas picks IADD3 on the ALU pipe),
+// 1 = every add as IMAD on the FMA pipe, 2 = hybrid: the two 3-input sums of a SHA round stay IADD3
+// (one ALU slot each, shortest critical path), everything else moves to the FMA pipe.
+#ifndef B200H_ADDMODE
+#define B200H_ADDMODE 1
+#endif
+#if B200H_ADDMODE == 0
+#define ADD(x, y) ((x) + (y))
+#else
+#define ADD(x, y) addf((x), (y), one)
+#endif
+#if B200H_ADDMODE == 2
+#define SHA_RND(a, b, c, d, e, f, g, h, K, W)                                  \
+    {                                                                          \
+        uint32_t t1 = ADD(h, ADD(W, K)) + SHA_S1(e) + lop3<0xCA>(e, f, g);     \
+        d = ADD(d, t1);                                                        \
+        h = t1 + SHA_S0(a) + lop3<0xE8>(a, b, c);                              \
     }
+#else
+#define SHA_RND(a, b, c, d, e, f, g, h, K, W)                                         \
+    {                                                                                 \
+        uint32_t t1 = ADD(ADD(ADD(h, ADD(W, K)), lop3<0xCA>(e, f, g)), SHA_S1(e));    \
+        uint32_t t2 = ADD(SHA_S0(a), lop3<0xE8>(a, b, c));                            \
+        d = ADD(d, t1);                                                               \
+        h = ADD(t1, t2);                                                              \
+    }
+#endif
 // message schedule in place: w[i&15] becomes W[i] for i >= 16
 #define SHA_SCHED(w, i) \
-    (w[(i)&15] += SHA_s1(w[((i)-2) & 15]) + w[((i)-7) & 15] + SHA_s0(w[((i)-15) & 15]))
+    (w[(i)&15] = ADD(ADD(ADD(w[(i)&15], w[((i)-7) & 15]), SHA_s0(w[((i)-15) & 15])), SHA_s1(w[((i)-2) & 15])))
 
 #define MD5_STEP(FN, a, b, c, d, xk, s, T)             \
     {                                                  \
-        a = b + rotl(a + FN(b, c, d) + (xk) + (T), s); \
+        a = ADD(b, rotl(ADD(ADD(a, ADD(xk, T)), FN(b, c, d)), s)); \
     }
 #define MD5_F(b, c, d) lop3<0xCA>(b, c, d)
 #define MD5_G(b, c, d) lop3<0xE4>(b, c, d)
@@ -95,7 +122,7 @@ __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0,
 // interleaved at source level (4 SHA rounds : 4 MD5 steps) to give every warp two chains of ILP.
 template <bool DO_SHA, bool DO_MD5>
 __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], const uint32_t (&x)[16],
-                                         bool is_last, uint32_t bits_lo, uint32_t bits_hi) {
+                                         bool is_last, uint32_t bits_lo, uint32_t bits_hi, uint32_t one) {
     uint32_t w[16];
     uint32_t m14 = x[14], m15 = x[15];
     if (DO_SHA) {
@@ -122,15 +149,15 @@ __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], c
             SHA_SCHED(w, (i) + 3);                              \
         }                                                       \
         if (((i)&7) == 0) {                                     \
-            SHA_RND(a, b, c, d, e, f, g, h, k0 + w[(i)&15]);    \
-            SHA_RND(h, a, b, c, d, e, f, g, k1 + w[((i) + 1) & 15]); \
-            SHA_RND(g, h, a, b, c, d, e, f, k2 + w[((i) + 2) & 15]); \
-            SHA_RND(f, g, h, a, b, c, d, e, k3 + w[((i) + 3) & 15]); \
+            SHA_RND(a, b, c, d, e, f, g, h, k0, w[(i)&15]);    \
+            SHA_RND(h, a, b, c, d, e, f, g, k1, w[((i) + 1) & 15]); \
+            SHA_RND(g, h, a, b, c, d, e, f, k2, w[((i) + 2) & 15]); \
+            SHA_RND(f, g, h, a, b, c, d, e, k3, w[((i) + 3) & 15]); \
         } else {                                                \
-            SHA_RND(e, f, g, h, a, b, c, d, k0 + w[(i)&15]);    \
-            SHA_RND(d, e, f, g, h, a, b, c, k1 + w[((i) + 1) & 15]); \
-            SHA_RND(c, d, e, f, g, h, a, b, k2 + w[((i) + 2) & 15]); \
-            SHA_RND(b, c, d, e, f, g, h, a, k3 + w[((i) + 3) & 15]); \
+            SHA_RND(e, f, g, h, a, b, c, d, k0, w[(i)&15]);    \
+            SHA_RND(d, e, f, g, h, a, b, c, k1, w[((i) + 1) & 15]); \
+            SHA_RND(c, d, e, f, g, h, a, b, k2, w[((i) + 2) & 15]); \
+            SHA_RND(b, c, d, e, f, g, h, a, k3, w[((i) + 3) & 15]); \
         }                                                       \
     }
 #define MD4(FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3) \
@@ -187,6 +214,9 @@ __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], c
 
 // ------------------------------------------------------------------------------ lane_hash_kernel
 
+#ifndef B200H_LANE_MIN_CTAS
+#define B200H_LANE_MIN_CTAS 5  // 20 warps/SM (96 registers/thread); 6 was measured 8% slower per block
+#endif
 constexpr int kLaneThreads = 128;  // 4 warps; every warp runs an independent TMA/mbarrier ring
 constexpr int kLaneWarps = kLaneThreads / 32;
 constexpr int kBPC = 2;     // 64-byte blocks per chunk (one bulk copy)
@@ -205,10 +235,11 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 }
 
 template <bool DO_SHA, bool DO_MD5>
-__global__ void __launch_bounds__(kLaneThreads, 5)
+__global__ void __launch_bounds__(kLaneThreads, B200H_LANE_MIN_CTAS)
 lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
                  const uint32_t* __restrict__ order, uint64_t n, uint32_t flags, int lanes_per_warp,
-                 uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out, ChainState* __restrict__ state) {
+                 uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out, ChainState* __restrict__ state,
+                 uint32_t one) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -330,7 +361,7 @@ lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
                     for (int k = 0; k < 16; ++k) x[k] = 0u;
                 }
                 const bool is_last = final && (step + 1 == nsteps);
-                compress<DO_SHA, DO_MD5>(hs, hm, x, is_last, bits_lo, bits_hi);
+                compress<DO_SHA, DO_MD5>(hs, hm, x, is_last, bits_lo, bits_hi, one);
             }
         }
         // the slot is private to this lane; order its generic-proxy reads before the async refill
@@ -543,7 +574,7 @@ static void launch_lane_t(int grid, const uint8_t* base, const uint64_t* off, co
                           const uint32_t* order, uint64_t n, uint32_t flags, int lpw, uint8_t* sha_out,
                           uint8_t* md5_out, ChainState* state, cudaStream_t st) {
     lane_hash_kernel<S, M><<<grid, kLaneThreads, kLaneSmem, st>>>(base, off, len, order, n, flags, lpw, sha_out,
-                                                                md5_out, state);
+                                                                md5_out, state, 1u);
 }
 
 int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* order,
