@@ -54,7 +54,7 @@ struct b200h_ctx {
     uint8_t* dwave[2] = {nullptr, nullptr};
     size_t dwave_cap = 0;  // per slot
     size_t dwave_want = 0;
-    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small;
+    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small, d_states;
     uint64_t* h_meta = nullptr;  // pinned: offsets then lengths
     size_t h_meta_cap = 0;       // in uint64 elements
     uint64_t launches = 0;
@@ -139,16 +139,6 @@ int ensure_meta(b200h_ctx* ctx, size_t elems) {
     return 0;
 }
 
-// lanes per warp: pack 32 messages per warp only when there are enough messages to fill the chip;
-// small batches spread one message per warp so every chain gets its own issue slots.
-int choose_lanes_per_warp(uint64_t n) {
-    const uint64_t target_warps = 148ull * 16ull;
-    uint64_t g = (n + target_warps - 1) / target_warps;
-    int lpw = 1;
-    while ((uint64_t)lpw < g && lpw < 32) lpw <<= 1;
-    return lpw;
-}
-
 int prof_begin(b200h_ctx* ctx, cudaStream_t st, cudaEvent_t* a, cudaEvent_t* b) {
     *a = *b = nullptr;
     if (!ctx->profiling) return 0;
@@ -189,17 +179,22 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     } else if (d_trim_out) {
         CU_TRY(ctx, cudaMemcpyAsync(d_trim_out, d_len, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     }
-    const uint32_t* order = nullptr;
-    if (n > 1) {
-        if (int rc = ensure_dev(ctx, ctx->d_order, n * sizeof(uint32_t))) return rc;
-        if (int rc = ensure_dev(ctx, ctx->d_scratch, (2 * kPlanBuckets + 2) * sizeof(uint32_t))) return rc;
-        ctx->launches += launch_plan(len_used, n, (uint32_t*)ctx->d_order.p, (uint32_t*)ctx->d_scratch.p, st);
-        order = (const uint32_t*)ctx->d_order.p;
+    // work queue (ring + control block) and chaining-state scratch for the persistent lane kernel
+    if (n >= 0x7fffffffull) return fail(ctx, B200H_E_INVALID, "batch larger than 2^31-2 messages");
+    if (int rc = ensure_dev(ctx, ctx->d_order, (size_t)ring_capacity(n) * sizeof(uint32_t))) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_scratch, (2 * kPlanBuckets + 8) * sizeof(uint32_t))) return rc;
+    uint32_t* ring = (uint32_t*)ctx->d_order.p;
+    uint32_t* scratch = (uint32_t*)ctx->d_scratch.p;
+    int* qctl = (int*)(scratch + 2 * kPlanBuckets);
+    ChainState* states = d_state;
+    if (!states) {
+        if (int rc = ensure_dev(ctx, ctx->d_states, n * sizeof(ChainState))) return rc;
+        states = (ChainState*)ctx->d_states.p;
     }
+    ctx->launches += launch_plan(len_used, n, ring, scratch, qctl, /*fresh=*/d_state == nullptr, st);
     cudaEvent_t pa, pb;
     if (int rc = prof_begin(ctx, st, &pa, &pb)) return rc;
-    ctx->launches += launch_lane_hash(d_base, d_off, len_used, order, n, kflags, choose_lanes_per_warp(n), d_sha,
-                                      d_md5, d_state, st);
+    ctx->launches += launch_lane_hash(d_base, d_off, len_used, ring, qctl, n, kflags, d_sha, d_md5, states, st);
     if (int rc = prof_end(ctx, st, pa, pb)) return rc;
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaEventRecord(ctx->ev_scratch, st));
@@ -454,7 +449,7 @@ void b200h_destroy(b200h_ctx* ctx) {
         cudaEventDestroy(pr.second);
     }
     for (DevBuf* b : {&ctx->d_off, &ctx->d_len, &ctx->d_order, &ctx->d_trim, &ctx->d_sha, &ctx->d_md5, &ctx->d_scratch,
-                      &ctx->d_small})
+                      &ctx->d_small, &ctx->d_states})
         if (b->p) cudaFree(b->p);
     for (int s = 0; s < 2; ++s) {
         if (ctx->dwave[s]) cudaFree(ctx->dwave[s]);

@@ -15,6 +15,8 @@
 //   fill_synth_kernel  counter-based synthetic bytes (bench/test data; same stream as synth.py).
 #include "b200hash_kernels.cuh"
 
+#include <cstdlib>
+
 namespace b200h {
 
 // ---------------------------------------------------------------------------------- PTX helpers
@@ -47,6 +49,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// Ampere-style per-thread async copy (SASS: LDGSTS): 16 bytes global -> shared, L1 bypassed.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -223,7 +234,7 @@ constexpr int kBPC = 2;     // 64-byte blocks per chunk (one bulk copy)
 constexpr int kStages = 2;  // chunks in flight per lane
 constexpr int kSlot = kBPC * 64 + 16;  // +16: holds the misaligned-start granule and de-conflicts LDS.128
 constexpr int kWarpSmem = kStages * 32 * kSlot;
-constexpr int kLaneSmem = kLaneWarps * kWarpSmem + kLaneWarps * kStages * 8;
+constexpr int kLaneSmem = kLaneWarps * kWarpSmem;
 
 __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 #pragma unroll
@@ -234,160 +245,239 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
     return v;
 }
 
+// Work queue shared by all persistent warps: a power-of-two ring of message ids in plan order (longest
+// first).  qctl[0] = entries available (signed), qctl[1] = head ticket, qctl[2] = tail ticket.
+// A FRESH entry starts from the IV; a re-queued entry resumes from its ChainState in st[].
+constexpr uint32_t kFresh = 0x80000000u;
+constexpr uint32_t kEmpty = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Persistent, time-sliced scheduling.  Every lane owns at most one message at a time and advances it by
+// one quantum (<= `quantum` 64-byte blocks, plus the padding blocks when the message ends).  At each quantum
+// boundary a warp whose lanes still hold unfinished messages puts them back on the queue *if other messages
+// are waiting* and pops the next ones, so n messages share S < n lanes evenly (no wave quantisation) and
+// mixed sizes balance like longest-first list scheduling.  Digest chaining state travels through st[].
 template <bool DO_SHA, bool DO_MD5>
 __global__ void __launch_bounds__(kLaneThreads, B200H_LANE_MIN_CTAS)
 lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
-                 const uint32_t* __restrict__ order, uint64_t n, uint32_t flags, int lanes_per_warp,
-                 uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out, ChainState* __restrict__ state,
-                 uint32_t one) {
+                 uint32_t* __restrict__ ring, uint32_t ring_mask, int* __restrict__ qctl, uint32_t flags,
+                 int lanes_per_warp, uint32_t quantum, uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out,
+                 ChainState* __restrict__ st, uint32_t one) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    uint8_t* ring = smem + wib * kWarpSmem;
-    const uint32_t bar0 = smem_u32(smem + kLaneWarps * kWarpSmem) + wib * kStages * 8;
-
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
-        fence_mbar_init();
-        fence_proxy_async();
-    }
-    __syncwarp();
-
-    // ---- which message does this lane own
-    const uint64_t wglobal = (uint64_t)blockIdx.x * kLaneWarps + wib;
-    const uint64_t slot_idx = wglobal * (uint64_t)lanes_per_warp + lane;
-    const bool active = lane < lanes_per_warp && slot_idx < n;
-    const uint32_t mi = active ? (order ? order[slot_idx] : (uint32_t)slot_idx) : 0u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint8_t* ring_smem = smem + wib * kWarpSmem;
     const bool final = !(flags & F_NO_FINAL);
+    const bool lane_on = lane < lanes_per_warp;
 
+    // ---- per-lane message context
+    bool has = false;
+    uint32_t mi = 0;
     const uint8_t* p = base;
-    uint64_t L = 0;
-    if (active) {
-        p = base + off[mi];
-        L = len[mi];
-    }
-    uint32_t hs[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,
-                      0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
-    uint32_t hm[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
-    uint64_t prior = 0;
-    if (state && active) {
-        const uint4* sp = reinterpret_cast<const uint4*>(&state[mi]);
-        uint4 q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3];
-        hs[0] = q0.x; hs[1] = q0.y; hs[2] = q0.z; hs[3] = q0.w;
-        hs[4] = q1.x; hs[5] = q1.y; hs[6] = q1.z; hs[7] = q1.w;
-        hm[0] = q2.x; hm[1] = q2.y; hm[2] = q2.z; hm[3] = q2.w;
-        prior = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
-    }
-    const uint64_t nfull = L >> 6;                      // blocks that stream through shared memory
-    const uint32_t r = final ? (uint32_t)(L & 63) : 0;  // bytes of the padded tail block
-    const uint32_t ntail = !active ? 0u : (final ? (r < 56 ? 1u : 2u) : 0u);
-    const uint64_t nsteps = nfull + ntail;
-    const uint64_t bits = (prior + L) << 3;
-    const uint32_t bits_lo = (uint32_t)bits, bits_hi = (uint32_t)(bits >> 32);
+    uint64_t L = 0, nfull = 0, done = 0, prior = 0;
+    uint32_t hs[8], hm[4];
 
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);  // misalignment of the message start
-    const uint8_t* p0 = p - mis;                                            // 16B-aligned copy source
-    const bool warp_aligned = __all_sync(0xffffffffu, mis == 0);
-    const uint64_t nchunks = (nfull + kBPC - 1) / kBPC;
-    const uint64_t max_chunks = warp_max_u64(nchunks);
-    const uint64_t max_outer = (warp_max_u64(nsteps) + kBPC - 1) / kBPC;
-
-    auto issue = [&](uint64_t c) {
-        const uint32_t st = (uint32_t)(c % kStages);
-        uint32_t bytes = 0;
-        if (c < nchunks) {
-            const uint64_t rem = nfull - c * kBPC;
-            bytes = (rem < kBPC ? (uint32_t)rem : (uint32_t)kBPC) * 64u + (mis ? 16u : 0u);
-        }
-        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
-        if (total == 0) return;
-        if (lane == 0) mbar_arrive_expect_tx(bar0 + 8 * st, total);
-        __syncwarp();
-        if (bytes) bulk_g2s(smem_u32(ring + (st * 32 + lane) * kSlot), p0 + c * (kBPC * 64), bytes, bar0 + 8 * st);
-    };
-
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) issue(s);
-
-    for (uint64_t c = 0; c < max_outer; ++c) {
-        const uint32_t st = (uint32_t)(c % kStages);
-        if (c < max_chunks) mbar_wait(bar0 + 8 * st, (uint32_t)((c / kStages) & 1));
-        const uint8_t* slot = ring + (st * 32 + lane) * kSlot;
-#pragma unroll 1
-        for (int j = 0; j < kBPC; ++j) {
-            const uint64_t step = c * kBPC + j;
-            if (step < nsteps) {
-                uint32_t x[16];
-                if (step < nfull) {
-                    const uint8_t* blk = slot + j * 64;
-                    if (warp_aligned) {
-                        const uint4* q = reinterpret_cast<const uint4*>(blk);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            uint4 v = q[k];
-                            x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
-                        }
-                    } else {
-                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(blk + (mis & ~3u));
-                        const uint32_t sh = (mis & 3u) * 8u;
-                        uint32_t y[17];
-#pragma unroll
-                        for (int k = 0; k < 17; ++k) y[k] = wp[k];
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) x[k] = __funnelshift_r(y[k], y[k + 1], sh);
-                    }
-                } else if (step == nfull) {
-                    // first tail block: the r leftover bytes straight from global (aligned 32-bit words,
-                    // only words that contain a message byte), then 0x80 and zero fill.
-                    const uint8_t* g = p + (nfull << 6);
-                    const uint32_t gm = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u);
-                    const uint32_t* gw = reinterpret_cast<const uint32_t*>(g - gm);
-                    const uint32_t span = r ? gm + r : 0u;  // bytes from gw to the end of the message
-                    uint32_t y[17];
-#pragma unroll
-                    for (int k = 0; k < 17; ++k) y[k] = (4u * k < span) ? __ldg(gw + k) : 0u;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        uint32_t v = __funnelshift_r(y[k], y[k + 1], gm * 8u);
-                        const int have = (int)r - 4 * k;  // message bytes in this word
-                        if (have <= 0) v = 0;
-                        else if (have < 4) v &= (1u << (8 * have)) - 1u;
-                        if (have >= 0 && have < 4) v |= 0x80u << (8 * have);
-                        x[k] = v;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) x[k] = 0u;
+    for (;;) {
+        // ------------------------------------------------------------ rotate: give waiting messages a turn
+        int waiting = 0;
+        if (lane == 0) waiting = *reinterpret_cast<volatile int*>(&qctl[0]);
+        waiting = __shfl_sync(0xffffffffu, waiting, 0);
+        const uint32_t has_mask = __ballot_sync(0xffffffffu, has);
+        if (waiting > 0 && has_mask) {
+            if (has) {
+                uint4* sp = reinterpret_cast<uint4*>(&st[mi]);
+                __stcg(sp + 0, make_uint4(hs[0], hs[1], hs[2], hs[3]));
+                __stcg(sp + 1, make_uint4(hs[4], hs[5], hs[6], hs[7]));
+                __stcg(sp + 2, make_uint4(hm[0], hm[1], hm[2], hm[3]));
+                __stcg(sp + 3, make_uint4((uint32_t)prior, (uint32_t)(prior >> 32), (uint32_t)done, (uint32_t)(done >> 32)));
+                __threadfence();
+            }
+            const int k = __popc(has_mask);
+            uint32_t t0 = 0;
+            if (lane == 0) t0 = atomicAdd(reinterpret_cast<unsigned int*>(&qctl[2]), (unsigned int)k);
+            t0 = __shfl_sync(0xffffffffu, t0, 0);
+            if (has) {
+                uint32_t* slot = ring + ((t0 + __popc(has_mask & lt_mask)) & ring_mask);
+                while (ld_volatile_u32(slot) != kEmpty) {
                 }
-                const bool is_last = final && (step + 1 == nsteps);
-                compress<DO_SHA, DO_MD5>(hs, hm, x, is_last, bits_lo, bits_hi, one);
+                st_volatile_u32(slot, mi);
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane == 0) atomicAdd(&qctl[0], k);
+            has = false;
+        }
+        // ------------------------------------------------------------ acquire
+        const uint32_t need_mask = __ballot_sync(0xffffffffu, lane_on && !has);
+        if (need_mask) {
+            const int need = __popc(need_mask);
+            int got = 0;
+            uint32_t h0 = 0;
+            if (lane == 0) {
+                const int old = atomicSub(&qctl[0], need);
+                got = old >= need ? need : (old > 0 ? old : 0);
+                if (got < need) atomicAdd(&qctl[0], need - got);
+                if (got) h0 = atomicAdd(reinterpret_cast<unsigned int*>(&qctl[1]), (unsigned int)got);
+            }
+            got = __shfl_sync(0xffffffffu, got, 0);
+            h0 = __shfl_sync(0xffffffffu, h0, 0);
+            if (lane_on && !has && __popc(need_mask & lt_mask) < got) {
+                uint32_t* slot = ring + ((h0 + __popc(need_mask & lt_mask)) & ring_mask);
+                uint32_t e;
+                while ((e = ld_volatile_u32(slot)) == kEmpty) {
+                }
+                st_volatile_u32(slot, kEmpty);
+                mi = e & ~kFresh;
+                has = true;
+                p = base + off[mi];
+                L = len[mi];
+                nfull = L >> 6;
+                if (e & kFresh) {
+                    hs[0] = 0x6a09e667u; hs[1] = 0xbb67ae85u; hs[2] = 0x3c6ef372u; hs[3] = 0xa54ff53au;
+                    hs[4] = 0x510e527fu; hs[5] = 0x9b05688cu; hs[6] = 0x1f83d9abu; hs[7] = 0x5be0cd19u;
+                    hm[0] = 0x67452301u; hm[1] = 0xefcdab89u; hm[2] = 0x98badcfeu; hm[3] = 0x10325476u;
+                    done = 0;
+                    prior = 0;
+                } else {
+                    __threadfence();
+                    const uint4* sp = reinterpret_cast<const uint4*>(&st[mi]);
+                    const uint4 q0 = __ldcg(sp + 0), q1 = __ldcg(sp + 1), q2 = __ldcg(sp + 2), q3 = __ldcg(sp + 3);
+                    hs[0] = q0.x; hs[1] = q0.y; hs[2] = q0.z; hs[3] = q0.w;
+                    hs[4] = q1.x; hs[5] = q1.y; hs[6] = q1.z; hs[7] = q1.w;
+                    hm[0] = q2.x; hm[1] = q2.y; hm[2] = q2.z; hm[3] = q2.w;
+                    prior = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
+                    done = (uint64_t)q3.z | ((uint64_t)q3.w << 32);
+                }
             }
         }
-        // the slot is private to this lane; order its generic-proxy reads before the async refill
-        fence_proxy_async();
-        __syncwarp();
-        if (c + kStages < max_chunks) issue(c + kStages);
-    }
+        if (!__any_sync(0xffffffffu, has)) break;
 
-    if (!active) return;
-    if (final) {
-        if (DO_SHA && sha_out) {
-            uint4* o = reinterpret_cast<uint4*>(sha_out + 32ull * mi);
-            o[0] = make_uint4(bswap(hs[0]), bswap(hs[1]), bswap(hs[2]), bswap(hs[3]));
-            o[1] = make_uint4(bswap(hs[4]), bswap(hs[5]), bswap(hs[6]), bswap(hs[7]));
+        // ------------------------------------------------------------ one quantum
+        const uint32_t r = final ? (uint32_t)(L & 63) : 0u;
+        uint32_t qblocks = 0, ntail = 0;
+        if (has) {
+            const uint64_t rem = nfull - done;
+            qblocks = rem < quantum ? (uint32_t)rem : quantum;
+            if (final && done + qblocks == nfull) ntail = r < 56 ? 1u : 2u;
         }
-        if (DO_MD5 && md5_out) {
-            *reinterpret_cast<uint4*>(md5_out + 16ull * mi) = make_uint4(hm[0], hm[1], hm[2], hm[3]);
+        const uint32_t nsteps = qblocks + ntail;
+        const uint64_t bits = (prior + L) << 3;
+        const uint32_t bits_lo = (uint32_t)bits, bits_hi = (uint32_t)(bits >> 32);
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
+        const uint8_t* src = p - mis + (done << 6);  // 16B-aligned source of this quantum's first block
+        const bool warp_aligned = __all_sync(0xffffffffu, mis == 0);
+        const uint32_t nchunks = (qblocks + kBPC - 1) / kBPC;
+        const uint32_t max_outer = (__reduce_max_sync(0xffffffffu, nsteps) + kBPC - 1) / kBPC;
+
+        // Each lane gathers its own chunk with 16-byte cp.async (LDGSTS) into its private slot; one commit
+        // group per chunk, so wait_group<kStages-1> means "my chunk c has landed".  No cross-lane sync.
+        auto issue = [&](uint32_t c) {
+            if (c < nchunks) {
+                const uint32_t rem = qblocks - c * kBPC;
+                const uint32_t pieces = (rem < (uint32_t)kBPC ? rem : (uint32_t)kBPC) * 4u + (mis ? 1u : 0u);
+                const uint32_t dst = smem_u32(ring_smem + ((c % kStages) * 32 + lane) * kSlot);
+                const uint8_t* g = src + c * (kBPC * 64);
+#pragma unroll
+                for (uint32_t k = 0; k < kBPC * 4 + 1; ++k)
+                    if (k < pieces) cp_async16(dst + 16 * k, g + 16 * k);
+            }
+            cp_async_commit();
+        };
+
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) issue(s);
+
+        for (uint32_t c = 0; c < max_outer; ++c) {
+            const uint32_t sidx = c % kStages;
+            cp_async_wait<kStages - 1>();
+            const uint8_t* slot = ring_smem + (sidx * 32 + lane) * kSlot;
+#pragma unroll 1
+            for (int j = 0; j < kBPC; ++j) {
+                const uint32_t step = c * kBPC + j;
+                if (step < nsteps) {
+                    uint32_t x[16];
+                    if (step < qblocks) {
+                        const uint8_t* blk = slot + j * 64;
+                        if (warp_aligned) {
+                            const uint4* q = reinterpret_cast<const uint4*>(blk);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                uint4 v = q[k];
+                                x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+                            }
+                        } else {
+                            const uint32_t* wp = reinterpret_cast<const uint32_t*>(blk + (mis & ~3u));
+                            const uint32_t sh = (mis & 3u) * 8u;
+                            uint32_t y[17];
+#pragma unroll
+                            for (int k = 0; k < 17; ++k) y[k] = wp[k];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) x[k] = __funnelshift_r(y[k], y[k + 1], sh);
+                        }
+                    } else if (step == qblocks) {
+                        // first padding block: the r leftover bytes straight from global (aligned 32-bit words,
+                        // only words that contain a message byte), then 0x80 and zero fill.
+                        const uint8_t* g = p + (nfull << 6);
+                        const uint32_t gm = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 3u);
+                        const uint32_t* gw = reinterpret_cast<const uint32_t*>(g - gm);
+                        const uint32_t span = r ? gm + r : 0u;  // bytes from gw to the end of the message
+                        uint32_t y[17];
+#pragma unroll
+                        for (int k = 0; k < 17; ++k) y[k] = (4u * k < span) ? __ldg(gw + k) : 0u;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            uint32_t v = __funnelshift_r(y[k], y[k + 1], gm * 8u);
+                            const int have = (int)r - 4 * k;  // message bytes in this word
+                            if (have <= 0) v = 0;
+                            else if (have < 4) v &= (1u << (8 * have)) - 1u;
+                            if (have >= 0 && have < 4) v |= 0x80u << (8 * have);
+                            x[k] = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) x[k] = 0u;
+                    }
+                    const bool is_last = ntail && (step + 1 == nsteps);
+                    compress<DO_SHA, DO_MD5>(hs, hm, x, is_last, bits_lo, bits_hi, one);
+                }
+            }
+            issue(c + kStages);  // refill the slot just consumed (an empty group when nothing is left)
         }
-    }
-    if (state && !final) {
-        uint4* sp = reinterpret_cast<uint4*>(&state[mi]);
-        const uint64_t np = prior + L;
-        sp[0] = make_uint4(hs[0], hs[1], hs[2], hs[3]);
-        sp[1] = make_uint4(hs[4], hs[5], hs[6], hs[7]);
-        sp[2] = make_uint4(hm[0], hm[1], hm[2], hm[3]);
-        sp[3] = make_uint4((uint32_t)np, (uint32_t)(np >> 32), 0u, 0u);
+        cp_async_wait<0>();
+
+        // ------------------------------------------------------------ retire finished messages
+        if (has) {
+            done += qblocks;
+            if (done == nfull) {
+                if (final) {
+                    if (DO_SHA && sha_out) {
+                        uint4* o = reinterpret_cast<uint4*>(sha_out + 32ull * mi);
+                        o[0] = make_uint4(bswap(hs[0]), bswap(hs[1]), bswap(hs[2]), bswap(hs[3]));
+                        o[1] = make_uint4(bswap(hs[4]), bswap(hs[5]), bswap(hs[6]), bswap(hs[7]));
+                    }
+                    if (DO_MD5 && md5_out)
+                        *reinterpret_cast<uint4*>(md5_out + 16ull * mi) = make_uint4(hm[0], hm[1], hm[2], hm[3]);
+                } else {
+                    // continuation segment: hand the chaining state back to the caller
+                    uint4* sp = reinterpret_cast<uint4*>(&st[mi]);
+                    const uint64_t np = prior + L;
+                    sp[0] = make_uint4(hs[0], hs[1], hs[2], hs[3]);
+                    sp[1] = make_uint4(hs[4], hs[5], hs[6], hs[7]);
+                    sp[2] = make_uint4(hm[0], hm[1], hm[2], hm[3]);
+                    sp[3] = make_uint4((uint32_t)np, (uint32_t)(np >> 32), 0u, 0u);
+                }
+                has = false;
+            }
+        }
     }
 }
 
@@ -476,9 +566,16 @@ __global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, u
 }
 
 // hist[0..B) counts -> cursor[0..B) start positions, longest bucket first.  Single CTA of kPlanBuckets threads.
-__global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
+__global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, int* __restrict__ qctl,
+                                 uint32_t n) {
     __shared__ uint32_t sh[kPlanBuckets];
     const int t = threadIdx.x;
+    if (t == 0) {
+        qctl[0] = (int)n;  // entries available
+        qctl[1] = 0;       // head ticket
+        qctl[2] = (int)n;  // tail ticket
+        qctl[3] = 0;
+    }
     const int rev = kPlanBuckets - 1 - t;  // position in longest-first order
     sh[t] = hist[rev];
     __syncthreads();
@@ -492,7 +589,7 @@ __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __
 }
 
 __global__ void plan_scatter_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ cursor,
-                                    uint32_t* __restrict__ order) {
+                                    uint32_t* __restrict__ order, uint32_t tag) {
     // warp-aggregated atomics: lanes hitting the same bucket share one atomicAdd
     for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < n;
          i0 += (uint64_t)gridDim.x * blockDim.x) {
@@ -504,7 +601,7 @@ __global__ void plan_scatter_kernel(const uint64_t* __restrict__ len, uint64_t n
         uint32_t basepos = 0;
         if (ok && (threadIdx.x & 31) == leader) basepos = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
         basepos = __shfl_sync(0xffffffffu, basepos, leader);
-        if (ok) order[basepos + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u))] = (uint32_t)i;
+        if (ok) order[basepos + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u))] = (uint32_t)i | tag;
     }
 }
 
@@ -558,37 +655,61 @@ int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, u
     return 1;
 }
 
-int launch_plan(const uint64_t* len, uint64_t n, uint32_t* order, uint32_t* scratch, cudaStream_t st) {
+static int g_sm_count = 148;
+static int g_lane_ctas_per_sm = B200H_LANE_MIN_CTAS;
+
+uint32_t ring_capacity(uint64_t n) {
+    uint32_t cap = 32;
+    while (cap < n) cap <<= 1;
+    return cap;
+}
+
+// Builds the work queue for the lane kernel: ring[0..n) = message ids bucketed longest-first (tagged FRESH
+// unless the batch resumes from caller-provided chaining states), ring[n..cap) = EMPTY, qctl = {n, 0, n}.
+int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* scratch, int* qctl, bool fresh,
+                cudaStream_t st) {
     if (!n) return 0;
     uint32_t* hist = scratch;
     uint32_t* cursor = scratch + kPlanBuckets;
     cudaMemsetAsync(hist, 0, sizeof(uint32_t) * kPlanBuckets, st);
+    cudaMemsetAsync(ring, 0xff, sizeof(uint32_t) * ring_capacity(n), st);
     plan_hist_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, hist);
-    plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor);
-    plan_scatter_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, cursor, order);
+    plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor, qctl, (uint32_t)n);
+    plan_scatter_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, cursor, ring, fresh ? kFresh : 0u);
     return 3;
 }
 
 template <bool S, bool M>
-static void launch_lane_t(int grid, const uint8_t* base, const uint64_t* off, const uint64_t* len,
-                          const uint32_t* order, uint64_t n, uint32_t flags, int lpw, uint8_t* sha_out,
+static void launch_lane_t(int grid, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring,
+                          uint32_t ring_mask, int* qctl, uint32_t flags, int lpw, uint32_t quantum, uint8_t* sha_out,
                           uint8_t* md5_out, ChainState* state, cudaStream_t st) {
-    lane_hash_kernel<S, M><<<grid, kLaneThreads, kLaneSmem, st>>>(base, off, len, order, n, flags, lpw, sha_out,
-                                                                md5_out, state, 1u);
+    lane_hash_kernel<S, M><<<grid, kLaneThreads, kLaneSmem, st>>>(base, off, len, ring, ring_mask, qctl, flags, lpw,
+                                                                quantum, sha_out, md5_out, state, 1u);
 }
 
-int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* order,
-                     uint64_t n, uint32_t flags, int lpw, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
+// Persistent launch: at most one resident wave of CTAs; lanes pull messages from the queue until it drains.
+// When the batch has fewer messages than resident lanes, messages are spread one-per-warp first
+// (lanes_per_warp < 32) so that every chain gets its own issue slots.
+int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring, int* qctl,
+                     uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
                      cudaStream_t st) {
     if (!n) return 0;
-    if (lpw < 1) lpw = 1;
-    if (lpw > 32) lpw = 32;
-    const uint64_t warps = (n + lpw - 1) / lpw;
-    const uint64_t grid = (warps + kLaneWarps - 1) / kLaneWarps;
+    const uint64_t resident_warps = (uint64_t)g_sm_count * g_lane_ctas_per_sm * kLaneWarps;
+    int lpw = 1;
+    while ((uint64_t)lpw * resident_warps < n && lpw < 32) lpw <<= 1;
+    uint64_t warps = (n + lpw - 1) / lpw;
+    if (warps > resident_warps) warps = resident_warps;
+    const int grid = (int)((warps + kLaneWarps - 1) / kLaneWarps);
+    const uint32_t mask = ring_capacity(n) - 1;
+    static const uint32_t quantum = [] {
+        const char* e = getenv("B200H_QUANTUM");  // tuning knob (blocks per time slice)
+        const long v = e ? atol(e) : 0;
+        return (uint32_t)(v > 0 ? v : 32);
+    }();
     const bool s = flags & F_SHA256, m = flags & F_MD5;
-    if (s && m) launch_lane_t<true, true>((int)grid, base, off, len, order, n, flags, lpw, sha_out, md5_out, state, st);
-    else if (s) launch_lane_t<true, false>((int)grid, base, off, len, order, n, flags, lpw, sha_out, md5_out, state, st);
-    else if (m) launch_lane_t<false, true>((int)grid, base, off, len, order, n, flags, lpw, sha_out, md5_out, state, st);
+    if (s && m) launch_lane_t<true, true>(grid, base, off, len, ring, mask, qctl, flags, lpw, quantum, sha_out, md5_out, state, st);
+    else if (s) launch_lane_t<true, false>(grid, base, off, len, ring, mask, qctl, flags, lpw, quantum, sha_out, md5_out, state, st);
+    else if (m) launch_lane_t<false, true>(grid, base, off, len, ring, mask, qctl, flags, lpw, quantum, sha_out, md5_out, state, st);
     else return 0;
     return 1;
 }
@@ -614,11 +735,21 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(lane_hash_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lane_hash_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
-    return e;
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0, ctas = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, lane_hash_kernel<true, true>, kLaneThreads, kLaneSmem);
+    if (e != cudaSuccess) return e;
+    if (sms > 0) g_sm_count = sms;
+    if (ctas > 0) g_lane_ctas_per_sm = ctas;
+    return cudaSuccess;
 }
 
 const char* kernel_build_info() {
-    return "b200hash kernels: sm_100a, lane_hash(threads=128, blocks/chunk=2, stages=2, slot=144B), " __DATE__;
+    return "b200hash kernels: sm_100a, lane_hash(persistent, time-sliced q=32, cp.async ring 2x128B per lane), " __DATE__;
 }
 
 }  // namespace b200h

@@ -26,11 +26,12 @@ constexpr int kPlanBuckets = 512;
 // Every wrapper returns the number of kernels it launched (for gpu_launches accounting).
 int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n, uint64_t* trimmed,
                 cudaStream_t st);
-int launch_plan(const uint64_t* len, uint64_t n, uint32_t* order, uint32_t* hist_scratch /*2*kPlanBuckets+2*/,
-                cudaStream_t st);
-int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* order,
-                     uint64_t n, uint32_t flags, int lanes_per_warp, uint8_t* sha_out, uint8_t* md5_out,
-                     ChainState* state, cudaStream_t st);
+uint32_t ring_capacity(uint64_t n);  // power of two >= max(n, 32): entries of the work-queue ring
+int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring /*ring_capacity(n)*/,
+                uint32_t* hist_scratch /*2*kPlanBuckets*/, int* qctl /*4*/, bool fresh, cudaStream_t st);
+int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring, int* qctl,
+                     uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out,
+                     ChainState* state /*n entries: caller states (F_NO_FINAL / resume) or scratch*/, cudaStream_t st);
 int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t start, cudaStream_t st);
 int launch_iota_parts(uint64_t* off, uint64_t* len, uint64_t total, uint64_t part_len, uint64_t nparts,
                       cudaStream_t st);
