@@ -1,0 +1,47 @@
+"""The two asyncio helpers the upload path needs (cf. py/modal/_utils/async_utils.py:345-433,593-624)."""
+from __future__ import annotations
+
+import asyncio
+import contextlib
+import functools
+import os
+
+
+def retry(n_attempts: int = 3, base_delay: float = 0.0, delay_factor: float = 2.0):
+    """Retry an async function with exponential backoff; the last failure propagates.
+    ``RETRY_N_ATTEMPTS_OVERRIDE`` (tests) caps the attempt count, as in the reference."""
+
+    def deco(fn):
+        @functools.wraps(fn)
+        async def wrapped(*args, **kwargs):
+            attempts = int(os.environ.get("RETRY_N_ATTEMPTS_OVERRIDE", n_attempts))
+            delay = base_delay
+            for attempt in range(attempts):
+                try:
+                    return await fn(*args, **kwargs)
+                except Exception:
+                    if attempt == attempts - 1:
+                        raise
+                    await asyncio.sleep(delay)
+                    delay *= delay_factor
+
+        return wrapped
+
+    return deco
+
+
+@contextlib.asynccontextmanager
+async def asyncnullcontext(*_args, **_kwargs):
+    yield
+
+
+async def gather_cancel_on_error(*coros):
+    """Run coroutines concurrently; on the first failure cancel the rest and re-raise."""
+    tasks = [asyncio.ensure_future(c) for c in coros]
+    try:
+        return await asyncio.gather(*tasks)
+    except BaseException:
+        for t in tasks:
+            t.cancel()
+        await asyncio.gather(*tasks, return_exceptions=True)
+        raise

@@ -1,0 +1,773 @@
+"""Drop-in for the hashing / chunking half of the reference's ``modal/_utils/blob_utils.py``.
+
+Same public names, size classes, thresholds and integrity checks as the reference
+(py/modal/_utils/blob_utils.py), with every digest produced by libb200hash on the B200:
+
+=============================  ===========================================================================
+reference (file:line)          here
+=============================  ===========================================================================
+``_get_file_upload_spec``      same semantics per file; ``get_file_upload_specs`` hashes a whole *list* of
+  :446-487                     files in one GPU batch (what ``Volume.batch_upload`` v1 / ``Mount`` need)
+``_gather_blocks`` … :622-705  one ``b200h_hash_fixed_parts(TRIM_ZEROS)`` call per file: the zero-trim scan and
+                               the SHA-256 of every 8 MiB block run on the device, the file is read ONCE
+``perform_multipart_upload``   all part MD5s + the md5-of-md5s ETag come from one GPU call before any byte is
+  :159-234                     sent; the per-chunk CPU re-hash inside the payload disappears
+``_blob_upload`` … :271-374    unchanged control flow (BlobCreate -> single PUT | multipart), GPU digests
+=============================  ===========================================================================
+
+Module constants stay patchable module globals read at call time, because the reference's tests patch
+them by dotted name (py/test/blob_test.py:57, py/test/volume_test.py:489).
+"""
+from __future__ import annotations
+
+import asyncio
+import dataclasses
+import mmap
+import os
+import platform
+import time
+from collections.abc import Callable, Sequence
+from contextlib import AbstractContextManager, asynccontextmanager, contextmanager
+from io import BytesIO, FileIO
+from pathlib import Path, PurePosixPath
+from typing import Any, BinaryIO, ContextManager
+from urllib.parse import urlparse
+
+import numpy as np
+
+from . import _lib, hash_utils
+from ._backend import get_context
+from ._logging import logger
+from ._wire import BlobCreateRequest
+from .async_utils import asyncnullcontext, gather_cancel_on_error, retry
+from .exception import ExecutionError
+from .hash_utils import UploadHashes, get_upload_hashes
+from .http_utils import ClientSessionRegistry
+
+MAX_OBJECT_SIZE_BYTES = 2 * 1024 * 1024  # function inputs/outputs above this go to blob storage
+MAX_ASYNC_OBJECT_SIZE_BYTES = 8 * 1024  # ... for async (spawn) calls
+LARGE_FILE_LIMIT = 4 * 1024 * 1024  # files at least this big are uploaded as blobs
+BLOB_MAX_PARALLELISM = 20
+DEFAULT_SEGMENT_CHUNK_SIZE = 2**24
+MULTIPART_UPLOAD_THRESHOLD = 1024**3  # above this no whole-file MD5 is computed (placeholder instead)
+MULTIPART_INFLIGHT_BYTES_MAX = 2 * 1024**3
+MULTIPART_INFLIGHT_BYTES_MIN = 256 * 1024 * 1024
+MULTIPART_INFLIGHT_MEMORY_FRACTION = 0.5
+BLOCK_SIZE: int = 8 * 1024 * 1024  # volumefs2 block
+SMALL_FILE_INLINE_LIMIT = 256 * 1024  # below this the content is cached in the spec
+_MD5_PLACEHOLDER = "baadbaad" * 4
+
+
+# --------------------------------------------------------------------------------------- byte budget
+
+
+class _ByteBudget:
+    """Caps the bytes in flight across concurrent part uploads (reference :66-91)."""
+
+    def __init__(self, total: int):
+        self._total = total
+        self._available = total
+        self._cond = asyncio.Condition()
+
+    @classmethod
+    def from_system_memory(cls) -> "_ByteBudget":
+        return cls(_get_multipart_inflight_budget())
+
+    @asynccontextmanager
+    async def acquire(self, n: int):
+        async with self._cond:
+            # a request larger than the whole budget is admitted once nothing else is in flight
+            await self._cond.wait_for(lambda: self._available >= min(n, self._total))
+            self._available -= n
+        try:
+            yield
+        finally:
+            async with self._cond:
+                self._available += n
+                self._cond.notify_all()
+
+
+def _get_multipart_inflight_budget() -> int:
+    try:
+        import psutil
+
+        available = psutil.virtual_memory().available
+    except Exception:
+        try:
+            available = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+        except (AttributeError, ValueError, OSError):
+            return MULTIPART_INFLIGHT_BYTES_MIN
+    want = int(available * MULTIPART_INFLIGHT_MEMORY_FRACTION)
+    return min(max(want, MULTIPART_INFLIGHT_BYTES_MIN), MULTIPART_INFLIGHT_BYTES_MAX)
+
+
+# ------------------------------------------------------------------------------ views of file contents
+
+
+@contextmanager
+def _readonly_view(fp: BinaryIO):
+    """uint8 ndarray over the whole content of ``fp`` without copying when possible:
+    BytesIO -> its buffer; real file -> a private read-only mmap; anything else -> one read()."""
+    if isinstance(fp, BytesIO):
+        buf = fp.getbuffer()
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        try:
+            yield arr
+        finally:
+            del arr
+            buf.release()  # callers drop their references first (see _with_view)
+        return
+    try:
+        fd = fp.fileno()
+        size = os.fstat(fd).st_size
+    except (OSError, AttributeError, ValueError):
+        fd, size = None, 0
+    if fd is not None and size > 0:
+        mm = mmap.mmap(fd, 0, access=mmap.ACCESS_READ)
+        try:
+            arr = np.frombuffer(mm, dtype=np.uint8)
+            yield arr
+            del arr
+        finally:
+            mm.close()
+        return
+    pos = fp.tell()
+    fp.seek(0)
+    data = fp.read()
+    fp.seek(pos)
+    yield np.frombuffer(data, dtype=np.uint8)
+
+
+def _with_view(fp: BinaryIO, fn):
+    """fn(view) over the content of ``fp``; the view is dropped before the underlying buffer is released,
+    so BytesIO objects stay closable/resizable afterwards."""
+    with _readonly_view(fp) as view:
+        try:
+            return fn(view)
+        finally:
+            del view
+
+
+# ------------------------------------------------------------------------------------ single-part PUT
+
+
+@retry(n_attempts=3, base_delay=0.3)
+async def _upload_to_s3_url(
+    upload_url,
+    payload,
+    content_md5_b64: str | None = None,
+    content_type: str | None = "application/octet-stream",
+) -> str:
+    """PUT one payload; returns the object's ETag after checking it against the local MD5
+    (reference :110-156: S3's single-part ETag is the quoted MD5 hex of the body)."""
+    with payload.reset_on_error():
+        headers = {}
+        if content_md5_b64 and use_md5(upload_url):
+            headers["Content-MD5"] = content_md5_b64
+        if content_type:
+            headers["Content-Type"] = content_type
+        async with ClientSessionRegistry.get_session().put(
+            upload_url, data=payload, headers=headers, skip_auto_headers=["content-type"] if content_type is None else []
+        ) as resp:
+            if resp.status == 503:  # S3 SlowDown
+                logger.debug("Received SlowDown signal from S3, sleeping for 1 second before retrying.")
+                await asyncio.sleep(1)
+            if resp.status != 200:
+                try:
+                    text = await resp.text()
+                except Exception:
+                    text = "<no body>"
+                raise ExecutionError(f"Put to url {upload_url} failed with status {resp.status}: {text}")
+            etag = resp.headers["ETag"].strip()
+            if etag[:2] in ("W/", "w/"):
+                etag = etag[2:]
+            if len(etag) >= 2 and etag[0] == '"' and etag[-1] == '"':
+                etag = etag[1:-1]
+            local_md5_hex = payload.md5_checksum().hexdigest()
+            if local_md5_hex != etag:
+                raise ExecutionError(f"Local data and remote data checksum mismatch ({local_md5_hex} vs {etag})")
+            return etag
+
+
+# ------------------------------------------------------------------------------------------ multipart
+
+
+def multipart_part_digests(data, part_length: int) -> tuple[list[bytes], str]:
+    """All part MD5s of ``data`` split every ``part_length`` bytes plus the expected combined ETag
+    ``md5(md5_0 || md5_1 || ...).hex() + "-<n>"`` -- one GPU call (reference :194-219 does n hashlib passes
+    on executor threads and one more on the loop thread)."""
+    _, md5, _, etag = get_context().hash_fixed_parts(data, part_length, _lib.MD5, want_etag=True)
+    parts = [md5[i].tobytes() for i in range(len(md5))]
+    return parts, f"{etag.hex()}-{len(parts)}"
+
+
+async def perform_multipart_upload(
+    data_file: BinaryIO | BytesIO | FileIO,
+    *,
+    content_length: int,
+    max_part_size: int,
+    part_urls: list[str],
+    completion_url: str,
+    upload_chunk_size: int = DEFAULT_SEGMENT_CHUNK_SIZE,
+    progress_report_cb: Callable | None = None,
+    byte_budget: _ByteBudget | None = None,
+) -> None:
+    from .bytes_io_segment_payload import BytesIOSegmentPayload
+
+    # 1. hash every part on the GPU before sending anything
+    start_pos = data_file.tell() if isinstance(data_file, BytesIO) else 0
+    part_md5, expected_etag = await asyncio.to_thread(
+        _with_view, data_file,
+        lambda whole: multipart_part_digests(whole[start_pos : start_pos + content_length], max_part_size))
+    if len(part_md5) > len(part_urls):
+        raise ExecutionError(f"{len(part_md5)} parts but only {len(part_urls)} part URLs")
+
+    # 2. one independent reader per part (no shared file position)
+    if isinstance(data_file, BytesIO):
+        view = data_file.getbuffer()
+        readers: list[BinaryIO] = [BytesIO(view) for _ in part_urls]
+        for rdr in readers:
+            rdr.seek(start_pos)
+    else:
+        readers = [open(data_file.name, "rb") for _ in part_urls]
+
+    async def send(url: str, payload) -> str:
+        async with byte_budget.acquire(4 * payload.chunk_size) if byte_budget else asyncnullcontext():
+            return await _upload_to_s3_url(url, payload=payload, content_type=None)
+
+    jobs, offset, left = [], 0, content_length
+    for i, (rdr, url) in enumerate(zip(readers, part_urls)):
+        n = min(left, max_part_size)
+        payload = BytesIOSegmentPayload(rdr, segment_start=offset, segment_length=n, chunk_size=upload_chunk_size,
+                                        progress_report_cb=progress_report_cb,
+                                        md5_digest=part_md5[i] if i < len(part_md5) else None)
+        jobs.append(send(url, payload))
+        offset += n
+        left -= n
+    try:
+        part_etags = await gather_cancel_on_error(*jobs)
+    finally:
+        if not isinstance(data_file, BytesIO):
+            for rdr in readers:
+                rdr.close()
+
+    xml = ["<CompleteMultipartUpload>"]
+    for number, etag in enumerate(part_etags, 1):
+        xml.append(f'<Part>\n<PartNumber>{number}</PartNumber>\n<ETag>"{etag}"</ETag>\n</Part>')
+    xml.append("</CompleteMultipartUpload>")
+    # each part's ETag was already checked against the GPU digest in _upload_to_s3_url, so the device-side
+    # md5-of-md5s is exactly what the store must report for the assembled object
+    if len(part_md5) != len(part_etags):
+        expected_etag = _etag_from_part_hexes(part_etags)
+    resp = await ClientSessionRegistry.get_session().post(
+        completion_url, data="\n".join(xml).encode("ascii"), skip_auto_headers=["content-type"]
+    )
+    if resp.status != 200:
+        try:
+            msg = await resp.text()
+        except Exception:
+            msg = "<no body>"
+        raise ExecutionError(f"Error when completing multipart upload: {resp.status}\n{msg}")
+    body_text = await resp.text()
+    if expected_etag not in body_text:
+        raise ExecutionError(f"Hash mismatch on multipart upload assembly: {expected_etag} not in {body_text}")
+
+
+def _etag_from_part_hexes(part_etags: Sequence[str]) -> str:
+    raw = b"".join(bytes.fromhex(e) for e in part_etags)
+    _, md5, _ = get_context().hash_buffers([raw], _lib.MD5)
+    return f"{md5[0].tobytes().hex()}-{len(part_etags)}"
+
+
+# ---------------------------------------------------------------------------------------- blob upload
+
+
+def get_content_length(data: BinaryIO) -> int:
+    """Bytes from the current position to the end of the stream."""
+    here = data.tell()
+    end = data.seek(0, os.SEEK_END)
+    data.seek(here)
+    return end - here
+
+
+async def _blob_upload_with_fallback(items, blob_ids: list[str], callback, content_length: int) -> tuple[str, bool, int]:
+    """Try each storage provider in order; report whether R2 failed and the R2 throughput (reference :246-268)."""
+    r2_failed, r2_bps = False, 0
+    for idx, (item, blob_id) in enumerate(zip(items, blob_ids)):
+        is_r2 = blob_id.endswith(":r2")
+        try:
+            t0 = time.monotonic_ns()
+            await callback(item)
+            if is_r2:
+                r2_bps = (content_length * 1_000_000_000) // max(time.monotonic_ns() - t0, 1)
+            return blob_id, r2_failed, r2_bps
+        except Exception:
+            r2_failed = r2_failed or is_r2
+            if idx == len(items) - 1:
+                raise
+    raise ExecutionError("Failed to upload blob")
+
+
+async def _blob_upload(
+    upload_hashes: UploadHashes,
+    data: bytes | BinaryIO,
+    stub,
+    progress_report_cb: Callable | None = None,
+    byte_budget: _ByteBudget | None = None,
+) -> tuple[str, bool, int]:
+    if isinstance(data, bytes):
+        data = BytesIO(data)
+    content_length = get_content_length(data)
+    resp = await stub.BlobCreate(
+        BlobCreateRequest(
+            content_md5=upload_hashes.md5_base64,
+            content_sha256_base64=upload_hashes.sha256_base64,
+            content_length=content_length,
+        )
+    )
+    if resp.WhichOneof("upload_types_oneof") == "multiparts":
+
+        async def send_multipart(part):
+            return await perform_multipart_upload(
+                data,
+                content_length=content_length,
+                max_part_size=part.part_length,
+                part_urls=part.upload_urls,
+                completion_url=part.completion_url,
+                upload_chunk_size=DEFAULT_SEGMENT_CHUNK_SIZE,
+                progress_report_cb=progress_report_cb,
+                byte_budget=byte_budget,
+            )
+
+        result = await _blob_upload_with_fallback(resp.multiparts.items, resp.blob_ids, send_multipart, content_length)
+    else:
+        from .bytes_io_segment_payload import BytesIOSegmentPayload
+
+        # the whole-blob MD5 is already in upload_hashes: hand it to the payload instead of re-hashing
+        payload = BytesIOSegmentPayload(
+            data, segment_start=0, segment_length=content_length, progress_report_cb=progress_report_cb,
+            md5_digest=bytes.fromhex(upload_hashes.md5_hex()) if _is_real_md5(upload_hashes) else None,
+        )
+
+        async def send_single(url):
+            return await _upload_to_s3_url(url, payload, content_md5_b64=upload_hashes.md5_base64)
+
+        result = await _blob_upload_with_fallback(resp.upload_urls.items, resp.blob_ids, send_single, content_length)
+    if progress_report_cb:
+        progress_report_cb(complete=True)
+    return result
+
+
+def _is_real_md5(h: UploadHashes) -> bool:
+    return bool(h.md5_base64) and h.md5_hex() != _MD5_PLACEHOLDER
+
+
+async def blob_upload_with_r2_failure_info(payload: bytes, stub) -> tuple[str, bool, int]:
+    if isinstance(payload, str):
+        logger.debug("Blob uploading string, not bytes - auto-encoding as utf8")
+        payload = payload.encode("utf8")
+    t0 = time.time()
+    hashes = get_upload_hashes(payload)
+    out = await _blob_upload(hashes, payload, stub)
+    mib = len(payload) / (1 << 20)
+    dt = max(time.time() - t0, 0.001)
+    logger.debug(f"Uploaded large blob of size {mib:.2f} MiB ({mib / dt:.2f} MiB/s, total {dt:.2f}s). {out[0]}")
+    return out
+
+
+async def blob_upload(payload: bytes, stub) -> str:
+    blob_id, _, _ = await blob_upload_with_r2_failure_info(payload, stub)
+    return blob_id
+
+
+async def blob_upload_many(payloads: Sequence[bytes], stub, concurrency: int | None = None) -> list[tuple[str, bool, int]]:
+    """The batched form the map pump uses: hash all payloads in ONE GPU batch, then run the uploads with
+    the reference's concurrency (BLOB_MAX_PARALLELISM).  Order is preserved."""
+    payloads = [p.encode("utf8") if isinstance(p, str) else p for p in payloads]
+    hashes = await asyncio.to_thread(hash_utils.get_upload_hashes_many, payloads)
+    sem = asyncio.Semaphore(concurrency or BLOB_MAX_PARALLELISM)
+
+    async def one(h, p):
+        async with sem:
+            return await _blob_upload(h, p, stub)
+
+    return list(await gather_cancel_on_error(*(one(h, p) for h, p in zip(hashes, payloads))))
+
+
+async def format_blob_data(data: bytes, api_stub) -> dict[str, Any]:
+    return {"data_blob_id": await blob_upload(data, api_stub)} if len(data) > MAX_OBJECT_SIZE_BYTES else {"data": data}
+
+
+async def blob_upload_file(
+    file_obj: BinaryIO,
+    stub,
+    progress_report_cb: Callable | None = None,
+    sha256_hex: str | None = None,
+    md5_hex: str | None = None,
+    byte_budget: _ByteBudget | None = None,
+) -> str:
+    hashes = get_upload_hashes(file_obj, sha256_hex=sha256_hex, md5_hex=md5_hex)
+    blob_id, _, _ = await _blob_upload(hashes, file_obj, stub, progress_report_cb, byte_budget=byte_budget)
+    return blob_id
+
+
+# ------------------------------------------------------------------------------- FileUploadSpec (v1)
+
+
+@dataclasses.dataclass
+class FileUploadSpec:
+    source: Callable[[], AbstractContextManager | BinaryIO]
+    source_description: Any
+    source_is_path: bool
+    mount_filename: str
+
+    use_blob: bool
+    sha256_hex: str
+    md5_hex: str
+    mode: int  # permission bits (low 12 bits of st_mode)
+    size: int
+    content: bytes | None = None  # cached for very small files
+
+    def read_content(self) -> bytes:
+        with self.source() as fp:
+            fp.seek(0)
+            return fp.read()
+
+
+def _size_class(size: int) -> tuple[bool, bool, bool]:
+    """-> (use_blob, want_md5, cache_content) for a file of ``size`` bytes (reference :459-474)."""
+    if size >= LARGE_FILE_LIMIT:
+        return True, not (size > MULTIPART_UPLOAD_THRESHOLD), False
+    return False, True, size < SMALL_FILE_INLINE_LIMIT
+
+
+def _get_file_upload_spec(
+    source: Callable[[], AbstractContextManager | BinaryIO],
+    source_description: Any,
+    mount_filename: PurePosixPath,
+    mode: int,
+) -> FileUploadSpec:
+    content = None
+    with source() as fp:
+        size = fp.seek(0, os.SEEK_END)  # the current position is ignored: uploads start at 0
+        fp.seek(0)
+        use_blob, want_md5, cache = _size_class(size)
+        if cache:
+            content = fp.read()
+            hashes = get_upload_hashes(content)
+        else:
+            hashes = get_upload_hashes(fp, md5_hex=None if want_md5 else _MD5_PLACEHOLDER)
+    return FileUploadSpec(
+        source=source,
+        source_description=source_description,
+        source_is_path=isinstance(source_description, Path),
+        mount_filename=mount_filename.as_posix(),
+        use_blob=use_blob,
+        sha256_hex=hashes.sha256_hex(),
+        md5_hex=hashes.md5_hex(),
+        mode=mode & 0o7777,
+        size=size,
+        content=content,
+    )
+
+
+def _default_mode(filename: Path) -> int:
+    return os.stat(filename).st_mode & (0o7777 if platform.system() != "Windows" else 0o7755)
+
+
+def get_file_upload_spec_from_path(
+    filename: Path, mount_filename: PurePosixPath, mode: int | None = None
+) -> FileUploadSpec:
+    return _get_file_upload_spec(lambda: open(filename, "rb"), filename, mount_filename, mode or _default_mode(filename))
+
+
+def get_file_upload_spec_from_fileobj(fp: BinaryIO, mount_filename: PurePosixPath, mode: int) -> FileUploadSpec:
+    @contextmanager
+    def source():
+        fp.seek(0)
+        yield fp
+
+    return _get_file_upload_spec(source, str(fp), mount_filename, mode)
+
+
+def get_file_upload_specs(
+    files: Sequence[tuple[Path, PurePosixPath, int | None]],
+) -> list[FileUploadSpec]:
+    """Batched ``get_file_upload_spec_from_path``: every file of a ``Volume.batch_upload`` / ``Mount`` goes
+    to the GPU in one batch (the reference fans the per-file hashlib loops over a ThreadPoolExecutor,
+    py/modal/volume.py:1209-1216, py/modal/mount.py:467-485).  Files are mapped read-only, so the bytes
+    travel page cache -> pinned staging -> HBM once; nothing is read through Python.
+    Same size classes / placeholder-MD5 / content caching as ``_get_file_upload_spec``."""
+    if not files:
+        return []
+    ctx = get_context()
+    maps: list[mmap.mmap | None] = []
+    views: list[np.ndarray] = []
+    handles = []
+    sizes: list[int] = []
+    try:
+        for filename, _, _ in files:
+            f = open(filename, "rb")
+            handles.append(f)
+            size = os.fstat(f.fileno()).st_size
+            sizes.append(size)
+            if size:
+                mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+                maps.append(mm)
+                views.append(np.frombuffer(mm, dtype=np.uint8))
+            else:
+                maps.append(None)
+                views.append(np.zeros(0, np.uint8))
+        classes = [_size_class(s) for s in sizes]
+        # one fused SHA-256+MD5 batch for the files that need both, a SHA-only batch for the > 1 GiB class
+        both = [i for i, c in enumerate(classes) if c[1]]
+        sha_only = [i for i, c in enumerate(classes) if not c[1]]
+        sha_of: dict[int, bytes] = {}
+        md5_of: dict[int, bytes] = {}
+        if both:
+            sha, md5, _ = ctx.hash_buffers([views[i] for i in both], _lib.SHA256 | _lib.MD5)
+            for k, i in enumerate(both):
+                sha_of[i], md5_of[i] = sha[k].tobytes(), md5[k].tobytes()
+        if sha_only:
+            sha, _, _ = ctx.hash_buffers([views[i] for i in sha_only], _lib.SHA256)
+            for k, i in enumerate(sha_only):
+                sha_of[i] = sha[k].tobytes()
+        specs = []
+        for i, (filename, mount_filename, mode) in enumerate(files):
+            use_blob, want_md5, cache = classes[i]
+            specs.append(
+                FileUploadSpec(
+                    source=(lambda fn=filename: open(fn, "rb")),
+                    source_description=filename,
+                    source_is_path=isinstance(filename, Path),
+                    mount_filename=PurePosixPath(mount_filename).as_posix(),
+                    use_blob=use_blob,
+                    sha256_hex=sha_of[i].hex(),
+                    md5_hex=md5_of[i].hex() if want_md5 else _MD5_PLACEHOLDER,
+                    mode=(mode or _default_mode(Path(filename))) & 0o7777,
+                    size=sizes[i],
+                    content=views[i].tobytes() if cache else None,
+                )
+            )
+        return specs
+    finally:
+        views.clear()
+        for mm in maps:
+            if mm is not None:
+                try:
+                    mm.close()
+                except BufferError:
+                    pass
+        for f in handles:
+            f.close()
+
+
+# ---------------------------------------------------------------------------- FileUploadSpec2 (v2)
+
+_FileUploadSource2 = Callable[[], ContextManager[BinaryIO]]
+
+
+@dataclasses.dataclass
+class FileUploadBlock:
+    start: int  # inclusive byte offset of the block in the file
+    end: int  # exclusive end after dropping the block's trailing zero bytes
+    contents_sha256: bytes  # raw 32-byte SHA-256 of [start, end)
+
+
+def _blocks_of(view: np.ndarray) -> list[FileUploadBlock]:
+    """All ceil(size/BLOCK_SIZE) blocks of one file image: trim scan + SHA-256 per block on the device."""
+    if view.size == 0:
+        return []
+    sha, _, trimmed, _ = get_context().hash_fixed_parts(view, BLOCK_SIZE, _lib.SHA256 | _lib.TRIM_ZEROS)
+    return [
+        FileUploadBlock(start=i * BLOCK_SIZE, end=i * BLOCK_SIZE + int(trimmed[i]), contents_sha256=sha[i].tobytes())
+        for i in range(len(trimmed))
+    ]
+
+
+@dataclasses.dataclass
+class FileUploadSpec2:
+    source: _FileUploadSource2
+    source_description: str | Path
+
+    path: str
+    blocks: list[FileUploadBlock]  # 8 MiB blocks
+    mode: int
+    size: int
+
+    @staticmethod
+    async def from_path(
+        filename: Path, mount_filename: PurePosixPath, hash_semaphore: asyncio.Semaphore, mode: int | None = None
+    ) -> "FileUploadSpec2":
+        def source():
+            return open(filename, "rb")
+
+        return await FileUploadSpec2._create(source, filename, mount_filename, mode or _default_mode(filename),
+                                             hash_semaphore)
+
+    @staticmethod
+    async def from_fileobj(
+        source_fp: BinaryIO | BytesIO, mount_filename: PurePosixPath, hash_semaphore: asyncio.Semaphore, mode: int
+    ) -> "FileUploadSpec2":
+        try:
+            fileno = source_fp.fileno()
+
+            def source():
+                fp = os.fdopen(os.dup(fileno), "rb")
+                fp.seek(0)
+                return fp
+
+        except OSError:  # BytesIO-like: no descriptor
+            buffer = source_fp.getbuffer()
+
+            def source():
+                return BytesIO(buffer)
+
+        return await FileUploadSpec2._create(source, str(source), mount_filename, mode, hash_semaphore)
+
+    @staticmethod
+    async def _create(
+        source: _FileUploadSource2,
+        source_description: str | Path,
+        mount_filename: PurePosixPath,
+        mode: int,
+        hash_semaphore: asyncio.Semaphore,
+    ) -> "FileUploadSpec2":
+        with source() as fp:
+            size = fp.seek(0, os.SEEK_END)
+        blocks = await _gather_blocks(source, size, hash_semaphore)
+        return FileUploadSpec2(source=source, source_description=source_description, path=mount_filename.as_posix(),
+                               blocks=blocks, mode=mode & 0o7777, size=size)
+
+
+async def _gather_blocks(source: _FileUploadSource2, size: int, hash_semaphore: asyncio.Semaphore) -> list[FileUploadBlock]:
+    """Block list of one file.  The reference launches one thread task per block, each reading its block
+    twice (rstrip pass + SHA pass, :640-664); here the file image is handed to the GPU once and all its
+    blocks are trimmed and hashed by one batch."""
+    if size == 0:
+        return []
+
+    def run() -> list[FileUploadBlock]:
+        with source() as fp:
+            return _with_view(fp, lambda view: _blocks_of(view[:size]))
+
+    async with hash_semaphore:
+        return await asyncio.to_thread(run)
+
+
+def _read_range(source: _FileUploadSource2, start: int, end: int) -> bytes:
+    with source() as fp:
+        fp.seek(start)
+        out = bytearray()
+        while len(out) < end - start:
+            chunk = fp.read(end - start - len(out))
+            if not chunk:
+                break
+            out += chunk
+        return bytes(out)
+
+
+def _gather_block(source: _FileUploadSource2, block_idx: int) -> FileUploadBlock:
+    start = block_idx * BLOCK_SIZE
+    data = _read_range(source, start, start + BLOCK_SIZE)
+    sha, _, trimmed = get_context().hash_batch_host(np.frombuffer(data, dtype=np.uint8), [0], [len(data)],
+                                                    _lib.SHA256 | _lib.TRIM_ZEROS)
+    return FileUploadBlock(start=start, end=start + int(trimmed[0]), contents_sha256=sha[0].tobytes())
+
+
+def _hash_range_sha256(source: _FileUploadSource2, start, end) -> bytes:
+    data = _read_range(source, start, end)
+    sha, _, _ = get_context().hash_buffers([data], _lib.SHA256)
+    return sha[0].tobytes()
+
+
+def _find_end_of_block(source: _FileUploadSource2, start: int, end: int) -> int | None:
+    """Index just past the last non-zero byte of [start, end) -- ``start`` for an empty or all-zero range.
+    (The reference docstring's ``(…, 0, 3) -> 4`` example is stale: its code, like this, returns 3.)"""
+    data = _read_range(source, start, end)
+    if not data:
+        return start
+    _, _, trimmed = get_context().hash_batch_host(np.frombuffer(data, dtype=np.uint8), [0], [len(data)],
+                                                  _lib.SHA256 | _lib.TRIM_ZEROS)
+    return start + int(trimmed[0])
+
+
+async def file_upload_specs2(
+    files: Sequence[tuple[Path, PurePosixPath, int | None]],
+) -> list[FileUploadSpec2]:
+    """Batched ``FileUploadSpec2.from_path`` for a whole ``batch_upload``: the blocks of ALL files form one
+    GPU batch (so a tree of many small files is as efficient as one big file)."""
+    if not files:
+        return []
+
+    def run() -> list[FileUploadSpec2]:
+        ctx = get_context()
+        handles, maps, views, sizes = [], [], [], []
+        try:
+            for filename, _, _ in files:
+                f = open(filename, "rb")
+                handles.append(f)
+                size = os.fstat(f.fileno()).st_size
+                sizes.append(size)
+                if size:
+                    mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+                    maps.append(mm)
+                    views.append(np.frombuffer(mm, dtype=np.uint8))
+                else:
+                    maps.append(None)
+                    views.append(np.zeros(0, np.uint8))
+            # one message per block, addressed absolutely (base=None)
+            owner, addr, length = [], [], []
+            for i, v in enumerate(views):
+                for start in range(0, sizes[i], BLOCK_SIZE):
+                    owner.append(i)
+                    addr.append(v.ctypes.data + start)
+                    length.append(min(BLOCK_SIZE, sizes[i] - start))
+            per_file: list[list[FileUploadBlock]] = [[] for _ in files]
+            if owner:
+                sha, _, trimmed = ctx.hash_batch_host(None, np.array(addr, np.uint64), np.array(length, np.uint64),
+                                                      _lib.SHA256 | _lib.TRIM_ZEROS)
+                for k, i in enumerate(owner):
+                    start = len(per_file[i]) * BLOCK_SIZE
+                    per_file[i].append(FileUploadBlock(start, start + int(trimmed[k]), sha[k].tobytes()))
+            return [
+                FileUploadSpec2(
+                    source=(lambda fn=filename: open(fn, "rb")),
+                    source_description=filename,
+                    path=PurePosixPath(mount_filename).as_posix(),
+                    blocks=per_file[i],
+                    mode=(mode or _default_mode(Path(filename))) & 0o7777,
+                    size=sizes[i],
+                )
+                for i, (filename, mount_filename, mode) in enumerate(files)
+            ]
+        finally:
+            views.clear()
+            for mm in maps:
+                if mm is not None:
+                    try:
+                        mm.close()
+                    except BufferError:
+                        pass
+            for f in handles:
+                f.close()
+
+    return await asyncio.to_thread(run)
+
+
+def use_md5(url: str) -> bool:
+    """Attach Content-MD5 only for real S3 / R2 hosts (moto and local fakes reject it; reference :708-727)."""
+    host = urlparse(url).netloc.split(":")[0]
+    if host.endswith((".amazonaws.com", ".r2.cloudflarestorage.com")):
+        return True
+    if host == "localhost":
+        return False
+    try:
+        import ipaddress
+
+        addr = ipaddress.ip_address(host)
+        if addr.is_private or addr.is_loopback:
+            return False
+    except ValueError:
+        pass
+    raise Exception(f"Unknown S3 host: {host}")

@@ -1,0 +1,84 @@
+"""Test scaffolding: an oracle-backed stand-in for ``_lib.Context`` so that host-layer logic
+(size classes, stream semantics, multipart planning, sharding) can be exercised on machines without a
+GPU.  Lives in tests/ only; the product never falls back to it."""
+from __future__ import annotations
+
+import numpy as np
+
+from modal_client_b200 import _lib
+from oracle import c_oracle
+
+
+def _u8(b) -> np.ndarray:
+    return b if isinstance(b, np.ndarray) else np.frombuffer(b, dtype=np.uint8)
+
+
+class FakeStream:
+    def __init__(self, flags):
+        self.flags, self.buf = flags, bytearray()
+
+    def update(self, data):
+        self.buf += bytes(data)
+
+    def digests(self):
+        d = bytes(self.buf)
+        return (c_oracle.sha256(d) if self.flags & _lib.SHA256 else None, c_oracle.md5(d) if self.flags & _lib.MD5 else None)
+
+    def reset(self):
+        self.buf.clear()
+
+    def close(self):
+        pass
+
+
+class FakeContext:
+    device = -1
+
+    def __init__(self):
+        self.calls = []
+
+    def hash_buffers(self, bufs, flags=_lib.SHA256 | _lib.MD5):
+        self.calls.append(("hash_buffers", len(bufs), flags))
+        n = len(bufs)
+        sha = np.zeros((n, 32), np.uint8) if flags & _lib.SHA256 else None
+        md5 = np.zeros((n, 16), np.uint8) if flags & _lib.MD5 else None
+        ln = np.zeros(n, np.uint64)
+        for i, b in enumerate(bufs):
+            a = _u8(b)
+            ln[i] = a.size
+            if sha is not None:
+                sha[i] = np.frombuffer(c_oracle.sha256(a), np.uint8)
+            if md5 is not None:
+                md5[i] = np.frombuffer(c_oracle.md5(a), np.uint8)
+        return sha, md5, ln
+
+    def hash_batch_host(self, base, offsets, lengths, flags=_lib.SHA256 | _lib.MD5):
+        self.calls.append(("hash_batch_host", len(offsets), flags))
+        off = np.asarray(offsets, np.uint64)
+        ln = np.asarray(lengths, np.uint64)
+        if base is None:
+            import ctypes
+
+            bufs = [np.frombuffer((ctypes.c_uint8 * int(n)).from_address(int(o)), np.uint8) if n else np.zeros(0, np.uint8)
+                    for o, n in zip(off, ln)]
+            total = np.concatenate(bufs) if bufs else np.zeros(0, np.uint8)
+            pos = np.concatenate([[0], np.cumsum(ln)])[:-1].astype(np.uint64)
+            base, off = total, pos
+        s, m, e = c_oracle.hash_batch(_u8(base), off, ln, sha=bool(flags & _lib.SHA256), md5=bool(flags & _lib.MD5),
+                                      trim=bool(flags & _lib.TRIM_ZEROS))
+        return s, m, e
+
+    def hash_fixed_parts(self, data, part_len, flags=_lib.SHA256 | _lib.MD5, want_etag=False):
+        self.calls.append(("hash_fixed_parts", part_len, flags))
+        a = _u8(data)
+        starts = np.arange(0, a.size, part_len, dtype=np.uint64)
+        lens = np.minimum(part_len, a.size - starts).astype(np.uint64)
+        s, m, e = c_oracle.hash_batch(a, starts, lens, sha=bool(flags & _lib.SHA256), md5=bool(flags & _lib.MD5),
+                                      trim=bool(flags & _lib.TRIM_ZEROS))
+        etag = None
+        if want_etag:
+            etag = c_oracle.md5(m.tobytes() if m is not None and len(m) else b"")
+        return s, m, e, etag
+
+    def stream(self, flags=_lib.SHA256 | _lib.MD5):
+        return FakeStream(flags)
