@@ -129,6 +129,18 @@ __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0,
 #define MD5_H(b, c, d) lop3<0x96>(b, c, d)
 #define MD5_I(b, c, d) lop3<0x39>(b, c, d)
 
+#ifndef B200H_ROLLED
+#define B200H_ROLLED 0
+#endif
+// SHA-256 round constants for rounds 16..63 (used by the rolled variant)
+__constant__ uint32_t kShaK[48] = {
+    0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+    0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+    0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+    0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+    0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+
 // The two hashes are independent dependency chains over the same 16 words, so their rounds are
 // interleaved at source level (4 SHA rounds : 4 MD5 steps) to give every warp two chains of ILP.
 template <bool DO_SHA, bool DO_MD5>
@@ -187,6 +199,35 @@ __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], c
     MD4(MD5_F, x[8], x[9], x[10], x[11], 7, 12, 17, 22, 0x698098d8u, 0x8b44f7afu, 0xffff5bb1u, 0x895cd7beu)
     SHA4(12, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u)
     MD4(MD5_F, x[12], x[13], m14, m15, 7, 12, 17, 22, 0x6b901122u, 0xfd987193u, 0xa679438eu, 0x49b40821u)
+#if B200H_ROLLED
+    // Rounds 16..63 as three trips through one copy of the 16-round body (round constants from constant
+    // memory), MD5 rounds 2..4 selected per trip: halves the instruction footprint of the hot loop, which
+    // otherwise streams ~36 KB of code per block through the instruction caches.
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+        const uint32_t* kk = kShaK + 16 * it;
+        SHA4(16, kk[0], kk[1], kk[2], kk[3])
+        SHA4(20, kk[4], kk[5], kk[6], kk[7])
+        SHA4(24, kk[8], kk[9], kk[10], kk[11])
+        SHA4(28, kk[12], kk[13], kk[14], kk[15])
+        if (it == 0) {
+            MD4(MD5_G, x[1], x[6], x[11], x[0], 5, 9, 14, 20, 0xf61e2562u, 0xc040b340u, 0x265e5a51u, 0xe9b6c7aau)
+            MD4(MD5_G, x[5], x[10], m15, x[4], 5, 9, 14, 20, 0xd62f105du, 0x02441453u, 0xd8a1e681u, 0xe7d3fbc8u)
+            MD4(MD5_G, x[9], m14, x[3], x[8], 5, 9, 14, 20, 0x21e1cde6u, 0xc33707d6u, 0xf4d50d87u, 0x455a14edu)
+            MD4(MD5_G, x[13], x[2], x[7], x[12], 5, 9, 14, 20, 0xa9e3e905u, 0xfcefa3f8u, 0x676f02d9u, 0x8d2a4c8au)
+        } else if (it == 1) {
+            MD4(MD5_H, x[5], x[8], x[11], m14, 4, 11, 16, 23, 0xfffa3942u, 0x8771f681u, 0x6d9d6122u, 0xfde5380cu)
+            MD4(MD5_H, x[1], x[4], x[7], x[10], 4, 11, 16, 23, 0xa4beea44u, 0x4bdecfa9u, 0xf6bb4b60u, 0xbebfbc70u)
+            MD4(MD5_H, x[13], x[0], x[3], x[6], 4, 11, 16, 23, 0x289b7ec6u, 0xeaa127fau, 0xd4ef3085u, 0x04881d05u)
+            MD4(MD5_H, x[9], x[12], m15, x[2], 4, 11, 16, 23, 0xd9d4d039u, 0xe6db99e5u, 0x1fa27cf8u, 0xc4ac5665u)
+        } else {
+            MD4(MD5_I, x[0], x[7], m14, x[5], 6, 10, 15, 21, 0xf4292244u, 0x432aff97u, 0xab9423a7u, 0xfc93a039u)
+            MD4(MD5_I, x[12], x[3], x[10], x[1], 6, 10, 15, 21, 0x655b59c3u, 0x8f0ccc92u, 0xffeff47du, 0x85845dd1u)
+            MD4(MD5_I, x[8], m15, x[6], x[13], 6, 10, 15, 21, 0x6fa87e4fu, 0xfe2ce6e0u, 0xa3014314u, 0x4e0811a1u)
+            MD4(MD5_I, x[4], x[11], x[2], x[9], 6, 10, 15, 21, 0xf7537e82u, 0xbd3af235u, 0x2ad7d2bbu, 0xeb86d391u)
+        }
+    }
+#else
     SHA4(16, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu)
     MD4(MD5_G, x[1], x[6], x[11], x[0], 5, 9, 14, 20, 0xf61e2562u, 0xc040b340u, 0x265e5a51u, 0xe9b6c7aau)
     SHA4(20, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau)
@@ -211,6 +252,7 @@ __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], c
     MD4(MD5_I, x[8], m15, x[6], x[13], 6, 10, 15, 21, 0x6fa87e4fu, 0xfe2ce6e0u, 0xa3014314u, 0x4e0811a1u)
     SHA4(60, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u)
     MD4(MD5_I, x[4], x[11], x[2], x[9], 6, 10, 15, 21, 0xf7537e82u, 0xbd3af235u, 0x2ad7d2bbu, 0xeb86d391u)
+#endif
 #undef SHA4
 #undef MD4
 
@@ -694,11 +736,16 @@ int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* l
                      uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
                      cudaStream_t st) {
     if (!n) return 0;
+    // Lane packing.  A warp costs the same issue slots whether 1 or 32 of its lanes carry a message, and
+    // one warp alone on an SMSP is latency-bound (~0.27 IPC; measured), so: fill lanes first, but never use
+    // fewer warps than there are SMSPs (4 per SM) and never more than fit resident.
     const uint64_t resident_warps = (uint64_t)g_sm_count * g_lane_ctas_per_sm * kLaneWarps;
-    int lpw = 1;
-    while ((uint64_t)lpw * resident_warps < n && lpw < 32) lpw <<= 1;
-    uint64_t warps = (n + lpw - 1) / lpw;
+    const uint64_t min_warps = (uint64_t)g_sm_count * 4;
+    uint64_t warps = (n + 31) / 32;
+    if (warps < min_warps) warps = n < min_warps ? n : min_warps;
     if (warps > resident_warps) warps = resident_warps;
+    int lpw = (int)((n + warps - 1) / warps);
+    if (lpw > 32) lpw = 32;
     const int grid = (int)((warps + kLaneWarps - 1) / kLaneWarps);
     const uint32_t mask = ring_capacity(n) - 1;
     static const uint32_t quantum = [] {
