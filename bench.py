@@ -108,15 +108,26 @@ def run_cpu_pool(payloads: list[bytes], workers: int) -> float:
     return time.perf_counter() - t0
 
 
+def best_pool_workers(probe: list[bytes], repeats: int = 1) -> int:
+    """"All the host threads it can use": try the reference's default pool size (min(32, ncpu+4)), half and
+    all logical CPUs on a warm-up slice and keep the fastest (python thread pools do not scale to every core)."""
+    ncpu = os.cpu_count() or 1
+    workers, best = ncpu, None
+    for w in sorted({min(32, ncpu + 4), max(1, ncpu // 2), ncpu}):
+        for _ in range(repeats):
+            t = run_cpu_pool(probe, w)
+        if best is None or t < best:
+            workers, best = w, t
+    return workers
+
+
 def run_reference(args) -> None:
     rank, world, _ = env_rank()
     if rank != 0:
         return
-    workers = os.cpu_count() or 1
     sample_n = int(os.environ.get("B200H_REF_SAMPLE", 16384))  # 4 GiB of 256 KiB payloads per step
     payloads = cpu_payloads(sample_n, 0xB200)
-    for _ in range(args.warmup):
-        run_cpu_pool(payloads[: max(1024, sample_n // 8)], workers)
+    workers = best_pool_workers(payloads[: max(1024, sample_n // 4)], max(1, args.warmup))
     times = [run_cpu_pool(payloads, workers) for _ in range(args.steps)]
     total = sum(times)
     gibs = sample_n * MSG_BYTES * args.steps / GiB / total
@@ -139,7 +150,7 @@ def run_gpu(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from modal_client_b200 import _lib, batch
+    from modal_client_b200 import _lib, batch, sharding
 
     rank, world, local_rank = env_rank()
     torch.cuda.set_device(local_rank)
@@ -210,11 +221,17 @@ def run_gpu(args) -> None:
     off_h = (np.arange(N_MSG, dtype=np.uint64) * np.uint64(MSG_BYTES))
     len_h = np.full(N_MSG, MSG_BYTES, dtype=np.uint64)
     e2e_steps = max(1, min(args.steps, 3))
-    table = batch.hash_table_host(host, off_h, len_h, ctx=ctx)  # warm-up (allocates the wave buffers)
+    def e2e_step():
+        tab = batch.hash_table_host(host, off_h, len_h, ctx=ctx)
+        if world > 1:  # every rank ends the step holding the whole job's digest table
+            sharding.all_gather_table(tab.packed(), [N_MSG] * world, device=dev)
+        return tab
+
+    table = e2e_step()  # warm-up (allocates the wave buffers)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        table = batch.hash_table_host(host, off_h, len_h, ctx=ctx)
+        table = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -234,8 +251,7 @@ def run_gpu(args) -> None:
         sample_n = int(os.environ.get("B200H_CPU_SAMPLE", 16384))
         sample_n = min(sample_n, N_MSG)
         payloads = [host[i * MSG_BYTES:(i + 1) * MSG_BYTES].tobytes() for i in range(sample_n)]
-        workers = os.cpu_count() or 1
-        ref_port.hash_payloads_pool(payloads[:1024], workers)
+        workers = best_pool_workers(payloads[:4096])
         t0 = time.perf_counter()
         hashes = ref_port.hash_payloads_pool(payloads, workers)
         pool_s = time.perf_counter() - t0
@@ -278,7 +294,8 @@ def run_gpu(args) -> None:
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_value, 3), "unit": "GiB/s", "h2d_bytes_per_step": total_bytes + 16 * N_MSG,
                     "d2h_bytes_per_step": 56 * N_MSG, "steps": e2e_steps,
-                    "api": "modal_client_b200.batch.hash_table_host on page-locked host memory"},
+                    "api": "modal_client_b200.batch.hash_table_host on page-locked host memory"
+                           + (" + sharding.all_gather_table (NCCL)" if world > 1 else "")},
             "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
         }
         print(json.dumps(out))
