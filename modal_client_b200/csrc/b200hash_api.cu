@@ -43,7 +43,13 @@ struct b200h_ctx {
     int device = 0;
     std::mutex mu;
     std::string err;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_chain = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // The warp-specialised chain kernel (TMA tiles + mbarriers) is OFF by default: measured on B200 it loses to
+    // the lane kernel with packed lanes in every configuration tried (profiles/r1_chain_vs_lane.md) because a
+    // lone warp issues only ~0.27 IPC whatever it runs.  B200H_CHAIN=N (N>=1) routes up to N outliers to it.
+    bool chain_enabled = false;
+    uint32_t chain_cap = 296;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};    // H2D of a wave slot finished
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // kernels reading a wave slot finished
     cudaEvent_t ev_pin[2] = {nullptr, nullptr};       // H2D out of a pinned slot finished
@@ -182,20 +188,32 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     // work queue (ring + control block) and chaining-state scratch for the persistent lane kernel
     if (n >= 0x7fffffffull) return fail(ctx, B200H_E_INVALID, "batch larger than 2^31-2 messages");
     if (int rc = ensure_dev(ctx, ctx->d_order, (size_t)ring_capacity(n) * sizeof(uint32_t))) return rc;
-    if (int rc = ensure_dev(ctx, ctx->d_scratch, (2 * kPlanBuckets + 8) * sizeof(uint32_t))) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_scratch, (kPlanScratchWords + kMaxChain) * sizeof(uint32_t))) return rc;
     uint32_t* ring = (uint32_t*)ctx->d_order.p;
     uint32_t* scratch = (uint32_t*)ctx->d_scratch.p;
-    int* qctl = (int*)(scratch + 2 * kPlanBuckets);
+    uint32_t* chain_list = scratch + kPlanScratchWords;
+    int* qctl = plan_qctl(scratch);
     ChainState* states = d_state;
     if (!states) {
         if (int rc = ensure_dev(ctx, ctx->d_states, n * sizeof(ChainState))) return rc;
         states = (ChainState*)ctx->d_states.p;
     }
-    ctx->launches += launch_plan(len_used, n, ring, scratch, qctl, /*fresh=*/d_state == nullptr, st);
+    const bool resume = d_state != nullptr;
+    ctx->launches += launch_plan(len_used, n, ring, chain_list, scratch, /*fresh=*/!resume,
+                                 ctx->chain_enabled ? ctx->chain_cap : 0u, st);
+    if (ctx->chain_enabled) {
+        // outlier (long) messages run on the warp-specialised chain kernel, concurrently with the lane kernel
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_chain, ctx->ev_fork, 0));
+        ctx->launches += launch_chain_hash(d_base, d_off, len_used, chain_list, qctl, kflags, d_sha, d_md5, states,
+                                           resume, ctx->s_chain);
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->s_chain));
+    }
     cudaEvent_t pa, pb;
     if (int rc = prof_begin(ctx, st, &pa, &pb)) return rc;
     ctx->launches += launch_lane_hash(d_base, d_off, len_used, ring, qctl, n, kflags, d_sha, d_md5, states, st);
     if (int rc = prof_end(ctx, st, pa, pb)) return rc;
+    if (ctx->chain_enabled) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaEventRecord(ctx->ev_scratch, st));
     ctx->scratch_used = true;
@@ -422,6 +440,18 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
     CU_INIT(configure_kernels());
     CU_INIT(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
     CU_INIT(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CU_INIT(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU_INIT(cudaStreamCreateWithPriority(&ctx->s_chain, cudaStreamNonBlocking, hi));
+    }
+    CU_INIT(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CU_INIT(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    if (const char* e = getenv("B200H_CHAIN")) {  // tuning knob: 0 disables, N caps the chain-kernel share
+        const long v = atol(e);
+        ctx->chain_enabled = v > 0;
+        if (v > 1) ctx->chain_cap = (uint32_t)std::min<long>(v, (long)kMaxChain);
+    }
     for (int s = 0; s < 2; ++s) {
         CU_INIT(cudaEventCreateWithFlags(&ctx->ev_copied[s], cudaEventDisableTiming));
         CU_INIT(cudaEventCreateWithFlags(&ctx->ev_consumed[s], cudaEventDisableTiming));
@@ -462,6 +492,9 @@ void b200h_destroy(b200h_ctx* ctx) {
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_chain) cudaStreamDestroy(ctx->s_chain);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     cudaGetLastError();
     delete ctx;
 }

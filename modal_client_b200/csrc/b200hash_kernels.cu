@@ -523,6 +523,284 @@ lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------ chain_hash_kernel
+// One CTA per (long) message, three specialised warps, tiles of 32 blocks (2 KiB):
+//   warp 0  producer/expander: one elected lane streams the message into a 4-deep shared-memory tile ring
+//           with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP, mbarrier complete_tx); then all 32 lanes
+//           expand the SHA-256 message schedule of the tile's 32 blocks in parallel (lane = block) and store
+//           W[t]+K[t] rows for the chain warp.  The padding block(s) are synthesised into a final tile.
+//   warp 1  SHA-256 chain: one lane runs the 64 rounds per block straight from the W+K rows
+//           (10 ALU-pipe instructions per round: the serial floor of a single chain on one SMSP).
+//   warp 2  MD5 chain: one lane runs the 64 steps per block straight from the raw tile.
+// The three warps land on different SMSPs of the SM and hand tiles over through mbarriers only.
+
+constexpr int kChainThreads = 96;
+constexpr int kTileBlocks = 32;
+constexpr int kTileData = kTileBlocks * 64;
+constexpr int kTileStride = kTileData + 32;  // + the misaligned leading granule; keeps 16-byte alignment
+constexpr int kNT = 4;                        // raw tile ring depth
+constexpr int kWkRow = 64 * 4 + 16;           // 272 B: conflict-free STS.128 across lanes
+constexpr int kWkBuf = kTileBlocks * kWkRow;
+constexpr int kNW = 2;                        // W+K ring depth
+constexpr int kChainSmem = kNT * kTileStride + kNW * kWkBuf + (2 * kNT + 2 * kNW) * 8;
+
+__constant__ uint32_t kShaKAll[64] = {
+    0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+    0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+    0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+    0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+    0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+    0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+    0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// 16 little-endian message words of the 64-byte block at `blk + toff` (toff = 0..15 bytes of misalignment)
+__device__ __forceinline__ void load_block_words(const uint8_t* blk, uint32_t toff, uint32_t (&x)[16]) {
+    if (toff == 0) {
+        const uint4* q = reinterpret_cast<const uint4*>(blk);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 v = q[k];
+            x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+        }
+    } else {
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(blk + (toff & ~3u));
+        const uint32_t sh = (toff & 3u) * 8u;
+        uint32_t y[17];
+#pragma unroll
+        for (int k = 0; k < 17; ++k) y[k] = wp[k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = __funnelshift_r(y[k], y[k + 1], sh);
+    }
+}
+
+#define CH_RND(a, b, c, d, e, f, g, h, WK)                                            \
+    {                                                                                 \
+        uint32_t t1 = ADD(ADD(ADD(h, WK), lop3<0xCA>(e, f, g)), SHA_S1(e));           \
+        uint32_t t2 = ADD(SHA_S0(a), lop3<0xE8>(a, b, c));                            \
+        d = ADD(d, t1);                                                               \
+        h = ADD(t1, t2);                                                              \
+    }
+
+template <bool DO_SHA, bool DO_MD5>
+__global__ void __launch_bounds__(kChainThreads)
+chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
+                  const uint32_t* __restrict__ chain_list, const int* __restrict__ qctl, uint32_t flags,
+                  uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out, ChainState* __restrict__ st,
+                  int resume, uint32_t one) {
+    if ((int)blockIdx.x >= qctl[3]) return;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t* tiles = smem;
+    uint8_t* wkbuf = smem + kNT * kTileStride;
+    const uint32_t bars = smem_u32(smem + kNT * kTileStride + kNW * kWkBuf);
+    const uint32_t tile_full = bars, tile_free = bars + 8 * kNT, wk_full = bars + 16 * kNT, wk_free = bars + 16 * kNT + 8 * kNW;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kNT; ++i) {
+            mbar_init(tile_full + 8 * i, 1);
+            mbar_init(tile_free + 8 * i, (DO_SHA ? 1 : 0) + (DO_MD5 ? 1 : 0));
+        }
+        for (int i = 0; i < kNW; ++i) {
+            mbar_init(wk_full + 8 * i, 1);
+            mbar_init(wk_free + 8 * i, 1);
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const uint32_t mi = chain_list[blockIdx.x];
+    const uint8_t* p = base + off[mi];
+    const uint64_t L = len[mi];
+    const bool final = !(flags & F_NO_FINAL);
+    uint64_t prior = 0;
+    if (resume) prior = st[mi].prior_bytes;
+    const uint64_t nfull = L >> 6;
+    const uint32_t r = final ? (uint32_t)(L & 63) : 0u;
+    const uint32_t ntail = final ? (r < 56 ? 1u : 2u) : 0u;
+    const uint64_t t_data = (nfull + kTileBlocks - 1) / kTileBlocks;  // tiles streamed by TMA
+    const uint64_t t_all = t_data + (ntail ? 1 : 0);                  // + the synthesised padding tile
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
+    const uint8_t* p0 = p - mis;
+    const uint64_t bits = (prior + L) << 3;
+    const uint32_t bits_lo = (uint32_t)bits, bits_hi = (uint32_t)(bits >> 32);
+    auto blocks_in = [&](uint64_t t) -> uint32_t {
+        if (t < t_data) {
+            const uint64_t rem = nfull - t * kTileBlocks;
+            return rem < (uint64_t)kTileBlocks ? (uint32_t)rem : (uint32_t)kTileBlocks;
+        }
+        return ntail;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer / schedule expander
+        auto issue = [&](uint64_t t) {
+            const uint32_t slot = (uint32_t)(t % kNT);
+            mbar_wait(tile_free + 8 * slot, (uint32_t)(((t / kNT) & 1) ^ 1));
+            uint8_t* tile = tiles + slot * kTileStride;
+            if (t < t_data) {
+                if (lane == 0) {
+                    const uint32_t bytes = blocks_in(t) * 64u + (mis ? 16u : 0u);
+                    mbar_arrive_expect_tx(tile_full + 8 * slot, bytes);
+                    bulk_g2s(smem_u32(tile), p0 + t * kTileData, bytes, tile_full + 8 * slot);
+                }
+            } else {
+                // padding tile: r leftover bytes, 0x80, zeros, 64-bit length (MD5 layout; the SHA expander
+                // substitutes its own big-endian length words)
+                reinterpret_cast<uint32_t*>(tile)[lane] = 0u;
+                __syncwarp();
+                const uint8_t* g = p + (nfull << 6);
+                for (uint32_t i = lane; i < r; i += 32) tile[i] = g[i];
+                if (lane == 0) {
+                    tile[r] = 0x80;
+                    uint32_t* lenw = reinterpret_cast<uint32_t*>(tile + (ntail - 1) * 64 + 56);
+                    lenw[0] = bits_lo;
+                    lenw[1] = bits_hi;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tile_full + 8 * slot);
+            }
+        };
+        for (uint64_t t = 0; t < t_all && t < (uint64_t)(kNT - 1); ++t) issue(t);
+        for (uint64_t t = 0; t < t_all; ++t) {
+            if (t + kNT - 1 < t_all) issue(t + kNT - 1);
+            if (DO_SHA) {
+                const uint32_t slot = (uint32_t)(t % kNT), ws = (uint32_t)(t % kNW);
+                const uint32_t nb = blocks_in(t);
+                const uint32_t toff = t < t_data ? mis : 0u;
+                mbar_wait(tile_full + 8 * slot, (uint32_t)((t / kNT) & 1));
+                uint32_t x[16];
+                if ((uint32_t)lane < nb) load_block_words(tiles + slot * kTileStride + lane * 64, toff, x);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tile_free + 8 * slot);
+                mbar_wait(wk_free + 8 * ws, (uint32_t)(((t / kNW) & 1) ^ 1));
+                if ((uint32_t)lane < nb) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = bswap(x[i]);
+                    if (t >= t_data && (uint32_t)lane == ntail - 1) {
+                        w[14] = bits_hi;
+                        w[15] = bits_lo;
+                    }
+                    uint4* row = reinterpret_cast<uint4*>(wkbuf + ws * kWkBuf + lane * kWkRow);
+#pragma unroll
+                    for (int i = 0; i < 64; i += 4) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int tt = i + j;
+                            if (tt >= 16)
+                                w[tt & 15] = w[tt & 15] + SHA_s1(w[(tt - 2) & 15]) + w[(tt - 7) & 15] + SHA_s0(w[(tt - 15) & 15]);
+                            o[j] = w[tt & 15] + kShaKAll[tt];
+                        }
+                        row[i / 4] = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(wk_full + 8 * ws);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------- SHA-256 chain
+        if (!DO_SHA) return;
+        uint32_t hs[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,
+                          0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        if (resume && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hs[i] = st[mi].sha[i];
+        }
+        for (uint64_t t = 0; t < t_all; ++t) {
+            const uint32_t ws = (uint32_t)(t % kNW);
+            const uint32_t nb = blocks_in(t);
+            mbar_wait(wk_full + 8 * ws, (uint32_t)((t / kNW) & 1));
+            if (lane == 0) {
+#pragma unroll 1
+                for (uint32_t bidx = 0; bidx < nb; ++bidx) {
+                    const uint4* row = reinterpret_cast<const uint4*>(wkbuf + ws * kWkBuf + bidx * kWkRow);
+                    uint32_t k[64];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint4 v = row[i];
+                        k[4 * i] = v.x; k[4 * i + 1] = v.y; k[4 * i + 2] = v.z; k[4 * i + 3] = v.w;
+                    }
+                    uint32_t a = hs[0], b = hs[1], c = hs[2], d = hs[3], e = hs[4], f = hs[5], g = hs[6], h = hs[7];
+#pragma unroll
+                    for (int i = 0; i < 64; i += 8) {
+                        CH_RND(a, b, c, d, e, f, g, h, k[i]);
+                        CH_RND(h, a, b, c, d, e, f, g, k[i + 1]);
+                        CH_RND(g, h, a, b, c, d, e, f, k[i + 2]);
+                        CH_RND(f, g, h, a, b, c, d, e, k[i + 3]);
+                        CH_RND(e, f, g, h, a, b, c, d, k[i + 4]);
+                        CH_RND(d, e, f, g, h, a, b, c, k[i + 5]);
+                        CH_RND(c, d, e, f, g, h, a, b, k[i + 6]);
+                        CH_RND(b, c, d, e, f, g, h, a, k[i + 7]);
+                    }
+                    hs[0] += a; hs[1] += b; hs[2] += c; hs[3] += d;
+                    hs[4] += e; hs[5] += f; hs[6] += g; hs[7] += h;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(wk_free + 8 * ws);
+        }
+        if (lane == 0) {
+            if (final) {
+                if (sha_out) {
+                    uint4* o = reinterpret_cast<uint4*>(sha_out + 32ull * mi);
+                    o[0] = make_uint4(bswap(hs[0]), bswap(hs[1]), bswap(hs[2]), bswap(hs[3]));
+                    o[1] = make_uint4(bswap(hs[4]), bswap(hs[5]), bswap(hs[6]), bswap(hs[7]));
+                }
+            } else if (st) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) st[mi].sha[i] = hs[i];
+                st[mi].prior_bytes = prior + L;
+                st[mi].reserved = 0;
+            }
+        }
+    } else {
+        // ----------------------------------------------------------------------------------- MD5 chain
+        if (!DO_MD5) return;
+        uint32_t hm[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+        uint32_t unused[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (resume && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hm[i] = st[mi].md5[i];
+        }
+        for (uint64_t t = 0; t < t_all; ++t) {
+            const uint32_t slot = (uint32_t)(t % kNT);
+            const uint32_t nb = blocks_in(t);
+            const uint32_t toff = t < t_data ? mis : 0u;
+            mbar_wait(tile_full + 8 * slot, (uint32_t)((t / kNT) & 1));
+            if (lane == 0) {
+#pragma unroll 1
+                for (uint32_t bidx = 0; bidx < nb; ++bidx) {
+                    uint32_t x[16];
+                    load_block_words(tiles + slot * kTileStride + bidx * 64, toff, x);
+                    compress<false, true>(unused, hm, x, false, 0u, 0u, one);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tile_free + 8 * slot);
+        }
+        if (lane == 0) {
+            if (final) {
+                if (md5_out) *reinterpret_cast<uint4*>(md5_out + 16ull * mi) = make_uint4(hm[0], hm[1], hm[2], hm[3]);
+            } else if (st) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st[mi].md5[i] = hm[i];
+                if (!DO_SHA) {
+                    st[mi].prior_bytes = prior + L;
+                    st[mi].reserved = 0;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ trim_kernel
 // Reference semantics (blob_utils.py:667-705): index just past the last non-zero byte, 0 when the
 // message is empty or all zero.  One warp per message scanning backwards, 4 x 16 B per lane in flight.
@@ -596,28 +874,46 @@ __device__ __forceinline__ uint32_t plan_bucket(uint64_t len) {
     return b < (uint32_t)kPlanBuckets ? b : (uint32_t)kPlanBuckets - 1;
 }
 
-__global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ hist) {
+// smallest block count that maps to bucket b (inverse of plan_bucket)
+__device__ __forceinline__ uint64_t plan_bucket_min_blocks(uint32_t b) {
+    if (b < 16) return b;
+    const uint32_t e = (b - 16) / 8 + 4, mant = (b - 16) % 8;
+    return (uint64_t)(8 + mant) << (e - 3);
+}
+
+__global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ hist,
+                                 unsigned long long* __restrict__ total_blocks) {
     __shared__ uint32_t sh[kPlanBuckets];
+    __shared__ unsigned long long sh_total;
     for (int i = threadIdx.x; i < kPlanBuckets; i += blockDim.x) sh[i] = 0;
+    if (threadIdx.x == 0) sh_total = 0;
     __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&sh[plan_bucket(len[i])], 1u);
+    unsigned long long mine = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t l = len[i];
+        mine += (l >> 6) + 1;
+        atomicAdd(&sh[plan_bucket(l)], 1u);
+    }
+    atomicAdd(&sh_total, mine);
     __syncthreads();
     for (int i = threadIdx.x; i < kPlanBuckets; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    if (threadIdx.x == 0 && sh_total) atomicAdd(total_blocks, sh_total);
 }
 
-// hist[0..B) counts -> cursor[0..B) start positions, longest bucket first.  Single CTA of kPlanBuckets threads.
+// hist[0..B) counts -> cursor[0..B) start positions, longest bucket first; also decides how many of the
+// longest messages leave the lane queue for the chain kernel.  Single CTA of kPlanBuckets threads.
+//
+// Chain selection: a message is an outlier when hashing it on one lane (~29 MB/s) would outlast the whole
+// batch on the lane kernel (~700 GB/s), i.e. when its block count exceeds total_blocks / kChainRatio; it must
+// also be long enough (kChainMinBlocks) for the tile pipeline to pay off.  At most max_chain messages (the
+// longest) are taken.  qctl = {lane entries available, head, tail, chain count}.
 __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, int* __restrict__ qctl,
-                                 uint32_t n) {
+                                 const unsigned long long* __restrict__ total_blocks, uint32_t n, uint32_t max_chain) {
     __shared__ uint32_t sh[kPlanBuckets];
+    __shared__ uint32_t sh_chain;
     const int t = threadIdx.x;
-    if (t == 0) {
-        qctl[0] = (int)n;  // entries available
-        qctl[1] = 0;       // head ticket
-        qctl[2] = (int)n;  // tail ticket
-        qctl[3] = 0;
-    }
+    if (t == 0) sh_chain = 0;
     const int rev = kPlanBuckets - 1 - t;  // position in longest-first order
     sh[t] = hist[rev];
     __syncthreads();
@@ -628,10 +924,25 @@ __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __
         __syncthreads();
     }
     cursor[rev] = sh[t] - hist[rev];  // exclusive
+    unsigned long long thr = *total_blocks / kChainRatio;
+    if (thr < kChainMinBlocks) thr = kChainMinBlocks;
+    const bool mine = plan_bucket_min_blocks((uint32_t)rev) >= thr;
+    const bool next = rev > 0 && plan_bucket_min_blocks((uint32_t)rev - 1) >= thr;
+    if (mine && !next) sh_chain = sh[t];  // inclusive count of everything at least this long
+    __syncthreads();
+    if (t == 0) {
+        const uint32_t c = sh_chain < max_chain ? sh_chain : max_chain;
+        qctl[0] = (int)(n - c);  // lane-queue entries available
+        qctl[1] = 0;             // head ticket
+        qctl[2] = (int)(n - c);  // tail ticket
+        qctl[3] = (int)c;        // messages handed to the chain kernel
+    }
 }
 
 __global__ void plan_scatter_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ cursor,
-                                    uint32_t* __restrict__ order, uint32_t tag) {
+                                    uint32_t* __restrict__ ring, uint32_t* __restrict__ chain_list,
+                                    const int* __restrict__ qctl, uint32_t tag) {
+    const uint32_t nchain = (uint32_t)qctl[3];
     // warp-aggregated atomics: lanes hitting the same bucket share one atomicAdd
     for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < n;
          i0 += (uint64_t)gridDim.x * blockDim.x) {
@@ -643,7 +954,11 @@ __global__ void plan_scatter_kernel(const uint64_t* __restrict__ len, uint64_t n
         uint32_t basepos = 0;
         if (ok && (threadIdx.x & 31) == leader) basepos = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
         basepos = __shfl_sync(0xffffffffu, basepos, leader);
-        if (ok) order[basepos + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u))] = (uint32_t)i | tag;
+        if (ok) {
+            const uint32_t pos = basepos + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+            if (pos < nchain) chain_list[pos] = (uint32_t)i;
+            else ring[pos - nchain] = (uint32_t)i | tag;
+        }
     }
 }
 
@@ -706,19 +1021,45 @@ uint32_t ring_capacity(uint64_t n) {
     return cap;
 }
 
-// Builds the work queue for the lane kernel: ring[0..n) = message ids bucketed longest-first (tagged FRESH
-// unless the batch resumes from caller-provided chaining states), ring[n..cap) = EMPTY, qctl = {n, 0, n}.
-int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* scratch, int* qctl, bool fresh,
-                cudaStream_t st) {
+// Builds the work lists: chain_list[0..c) = the c longest outlier messages (see plan_scan_kernel) for the chain
+// kernel; ring[0..n-c) = the rest, bucketed longest-first (tagged FRESH unless the batch resumes from
+// caller-provided chaining states), ring[n-c..cap) = EMPTY; qctl = {n-c, 0, n-c, c}.
+int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* chain_list, uint32_t* scratch, bool fresh,
+                uint32_t max_chain, cudaStream_t st) {
     if (!n) return 0;
     uint32_t* hist = scratch;
     uint32_t* cursor = scratch + kPlanBuckets;
+    int* qctl = plan_qctl(scratch);
+    unsigned long long* total = reinterpret_cast<unsigned long long*>(scratch + 2 * kPlanBuckets + 4);
     cudaMemsetAsync(hist, 0, sizeof(uint32_t) * kPlanBuckets, st);
+    cudaMemsetAsync(total, 0, sizeof(unsigned long long), st);
     cudaMemsetAsync(ring, 0xff, sizeof(uint32_t) * ring_capacity(n), st);
-    plan_hist_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, hist);
-    plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor, qctl, (uint32_t)n);
-    plan_scatter_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, cursor, ring, fresh ? kFresh : 0u);
+    plan_hist_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, hist, total);
+    plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor, qctl, total, (uint32_t)n, max_chain);
+    plan_scatter_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, cursor, ring, chain_list, qctl,
+                                                                fresh ? kFresh : 0u);
     return 3;
+}
+
+// One CTA per chain-list entry; the grid is sized for the cap and surplus CTAs exit at once (the count lives
+// on the device, in qctl[3]).
+int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* chain_list,
+                      const int* qctl, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
+                      bool resume, cudaStream_t st) {
+    const bool s = flags & F_SHA256, m = flags & F_MD5;
+    const int grid = (int)kMaxChain;
+    if (s && m)
+        chain_hash_kernel<true, true><<<grid, kChainThreads, kChainSmem, st>>>(base, off, len, chain_list, qctl, flags,
+                                                                               sha_out, md5_out, state, resume, 1u);
+    else if (s)
+        chain_hash_kernel<true, false><<<grid, kChainThreads, kChainSmem, st>>>(base, off, len, chain_list, qctl, flags,
+                                                                                sha_out, md5_out, state, resume, 1u);
+    else if (m)
+        chain_hash_kernel<false, true><<<grid, kChainThreads, kChainSmem, st>>>(base, off, len, chain_list, qctl, flags,
+                                                                                sha_out, md5_out, state, resume, 1u);
+    else
+        return 0;
+    return 1;
 }
 
 template <bool S, bool M>

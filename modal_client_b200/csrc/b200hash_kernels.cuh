@@ -21,14 +21,23 @@ enum : uint32_t {
 };
 
 constexpr int kPlanBuckets = 512;
+constexpr unsigned long long kChainMinBlocks = 1024;  // 64 KiB: shorter messages never go to the chain kernel
+constexpr unsigned long long kChainRatio = 24000;     // lane kernel ~700 GB/s vs ~29 MB/s for one lane
+constexpr uint32_t kMaxChain = 1184;                  // 8 chain CTAs per SM
+constexpr int kPlanScratchWords = 2 * kPlanBuckets + 8;  // hist, cursor, qctl[4], total_blocks (u64), pad
 
 // Launch wrappers (defined in b200hash_kernels.cu).  All asynchronous on `st`.
 // Every wrapper returns the number of kernels it launched (for gpu_launches accounting).
 int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n, uint64_t* trimmed,
                 cudaStream_t st);
 uint32_t ring_capacity(uint64_t n);  // power of two >= max(n, 32): entries of the work-queue ring
-int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring /*ring_capacity(n)*/,
-                uint32_t* hist_scratch /*2*kPlanBuckets*/, int* qctl /*4*/, bool fresh, cudaStream_t st);
+// scratch layout (uint32 words): hist[kPlanBuckets] | cursor[kPlanBuckets] | qctl[4] | total_blocks (u64) | pad
+inline int* plan_qctl(uint32_t* scratch) { return reinterpret_cast<int*>(scratch + 2 * kPlanBuckets); }
+int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring /*ring_capacity(n)*/, uint32_t* chain_list /*kMaxChain*/,
+                uint32_t* scratch /*kPlanScratchWords*/, bool fresh, uint32_t max_chain, cudaStream_t st);
+int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* chain_list,
+                      const int* qctl, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
+                      bool resume, cudaStream_t st);
 int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring, int* qctl,
                      uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out,
                      ChainState* state /*n entries: caller states (F_NO_FINAL / resume) or scratch*/, cudaStream_t st);

@@ -164,3 +164,61 @@ def test_one_large_message_and_64bit_lengths(ctx):
     sha, md5, _ = ctx.hash_batch_host(data, [0], [n], BOTH)
     assert sha[0].tobytes() == hashlib.sha256(data).digest()
     assert md5[0].tobytes() == hashlib.md5(data).digest()
+
+
+def test_chain_kernel_long_messages_all_tail_shapes(ctx):
+    """Messages long enough to be routed to the warp-specialised chain kernel (>= 64 KiB and outliers of the
+    batch): every padding shape, tile-boundary lengths, misaligned starts, single-digest modes, trim."""
+    base_len = 1024 * 64  # 1024 blocks = 32 full tiles
+    extras = [0, 1, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 2047, 2048, 2049, 4096 + 56, 100_003]
+    lens = np.array([base_len + e for e in extras] + [300_000, 1 << 20], np.uint64)
+    offs = np.zeros_like(lens)
+    pos = 0
+    for i, n in enumerate(lens):
+        pos += i % 16  # every misalignment 0..15
+        offs[i] = pos
+        pos += int(n)
+    buf = synth_array(17, pos + 64).copy()
+    buf[int(offs[3] + lens[3]) - 70 : int(offs[3] + lens[3])] = 0  # trailing zeros on one message
+    for flags in (BOTH, _lib.SHA256, _lib.MD5, BOTH | _lib.TRIM_ZEROS):
+        sha, md5, trimmed = ctx.hash_batch_host(buf, offs, lens, flags)
+        s, m, e = c_oracle.hash_batch(buf, offs, lens, sha=bool(flags & _lib.SHA256), md5=bool(flags & _lib.MD5),
+                                      trim=bool(flags & _lib.TRIM_ZEROS))
+        assert np.array_equal(trimmed, e)
+        if s is not None:
+            assert np.array_equal(sha, s)
+        if m is not None:
+            assert np.array_equal(md5, m)
+
+
+def test_chain_and_lane_kernels_agree(ctx, monkeypatch):
+    """The opt-in warp-specialised chain kernel (B200H_CHAIN=N, TMA tiles + mbarriers) gives the same table as
+    the default lane kernel, for every padding shape / misalignment / digest mode."""
+    base_len = 1024 * 64
+    extras = [0, 1, 55, 56, 63, 64, 65, 120, 2047, 2048, 2049, 100_003]
+    lens = np.array([base_len + e for e in extras] + [70_000, 1 << 20, 5, 123_457, 999_999], np.uint64)
+    offs = np.zeros_like(lens)
+    pos = 0
+    for i, n in enumerate(lens):
+        pos += i % 16
+        offs[i] = pos
+        pos += int(n)
+    buf = synth_array(18, pos + 16)
+    monkeypatch.setenv("B200H_CHAIN", "1184")
+    c2 = _lib.Context(0, pinned_bytes=32 << 20, device_bytes=128 << 20)
+    try:
+        for flags in (BOTH, _lib.SHA256, _lib.MD5):
+            a = ctx.hash_batch_host(buf, offs, lens, flags)
+            b = c2.hash_batch_host(buf, offs, lens, flags)
+            s, m, _ = c_oracle.hash_batch(buf, offs, lens, sha=bool(flags & _lib.SHA256), md5=bool(flags & _lib.MD5))
+            for got in (a, b):
+                assert s is None or np.array_equal(got[0], s)
+                assert m is None or np.array_equal(got[1], m)
+        st = c2.stream(BOTH)  # streamed continuation goes through the chain kernel's resume path
+        data = synth_bytes(19, 3 * (1 << 20) + 5)
+        st.update(data)
+        sd, md = st.digests()
+        assert sd == c_oracle.sha256(data) and md == c_oracle.md5(data)
+        st.close()
+    finally:
+        c2.close()

@@ -76,6 +76,10 @@ void run(const char* name, int warps_per_smsp) {
 }
 
 int main() {
+    // one warp per SMSP: what a single instruction stream with plenty of ILP can issue
+    run<0>("IADD R,R,R", 1); run<1>("IMAD R,R,R(one),R", 1); run<3>("LOP3", 1); run<4>("SHF.W", 1);
+    run<6>("LOP3 + IMAD imm alt", 1); run<8>("SHF + IADD alt", 1);
+    run<0>("IADD R,R,R", 2); run<3>("LOP3", 2); run<6>("LOP3 + IMAD imm alt", 2);
     for (int w : {4, 8}) {
         if (w == 4) {
             run<0>("IADD R,R,R", 4); run<1>("IMAD R,R,R(one),R", 4); run<2>("IMAD R,R,imm3,R", 4); run<3>("LOP3", 4);
