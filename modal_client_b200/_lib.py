@@ -109,6 +109,13 @@ def load_library() -> ctypes.CDLL:
         return L
 
 
+# CPython keeps a bytes object's payload at a fixed offset behind its header; taking the address this way
+# avoids building one numpy view per payload (3 us each) when a batch holds 10^5..10^6 small payloads.
+_BYTES_HDR = bytes.__basicsize__ - 1
+_probe = b"b200hash-address-probe"
+_FAST_BYTES_ADDR = ctypes.string_at(id(_probe) + _BYTES_HDR, len(_probe)) == _probe
+
+
 def _np_ptr(a: np.ndarray | None):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
 
@@ -205,9 +212,14 @@ class Context:
     def hash_buffers(self, bufs: Sequence, flags: int = SHA256 | MD5):
         """Hash many separate bytes-like objects without packing them in Python: their addresses go to
         the library as absolute offsets (base=NULL) and it gathers them into its pinned staging ring."""
+        n = len(bufs)
+        if _FAST_BYTES_ADDR and all(type(b) is bytes for b in bufs):
+            off = np.fromiter((id(b) + _BYTES_HDR for b in bufs), dtype=np.uint64, count=n)
+            ln = np.fromiter((len(b) for b in bufs), dtype=np.uint64, count=n)
+            return self.hash_batch_host(None, off, ln, flags)  # `bufs` keeps the objects alive for the call
         views = [np.frombuffer(b, dtype=np.uint8) for b in bufs]
-        off = np.fromiter((v.ctypes.data if v.size else 0 for v in views), dtype=np.uint64, count=len(views))
-        ln = np.fromiter((v.size for v in views), dtype=np.uint64, count=len(views))
+        off = np.fromiter((v.ctypes.data if v.size else 0 for v in views), dtype=np.uint64, count=n)
+        ln = np.fromiter((v.size for v in views), dtype=np.uint64, count=n)
         out = self.hash_batch_host(None, off, ln, flags)
         del views
         return out

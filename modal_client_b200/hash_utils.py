@@ -113,7 +113,28 @@ def get_upload_hashes(
     return out
 
 
-def get_upload_hashes_many(payloads: Sequence[bytes], *, want_md5: bool = True) -> list[UploadHashes]:
+class _UploadHashesView(Sequence):
+    """Read-only sequence of ``UploadHashes`` over a digest table; rows are formatted on access, so a batch of
+    10^6 payloads does not pay 10^6 base64 round trips up front."""
+
+    def __init__(self, sha, md5, n: int):
+        self._sha, self._md5, self._n = sha, md5, n
+
+    def __len__(self) -> int:
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return UploadHashes(md5_base64=_b64(self._md5[i].tobytes()) if self._md5 is not None else "",
+                            sha256_base64=_b64(self._sha[i].tobytes()))
+
+
+def get_upload_hashes_many(payloads: Sequence[bytes], *, want_md5: bool = True) -> Sequence[UploadHashes]:
     """N in-memory payloads -> N UploadHashes in ONE GPU batch.  This replaces the serial
     ``get_upload_hashes(payload)`` loop the map pump runs on its event-loop thread
     (py/modal/_utils/blob_utils.py:345 under parallel_map.py:139) and Go's per-call md5.Sum/sha256.Sum256
@@ -122,7 +143,4 @@ def get_upload_hashes_many(payloads: Sequence[bytes], *, want_md5: bool = True) 
         return []
     flags = SHA256 | (MD5 if want_md5 else 0)
     sha, md5, _ = get_context().hash_buffers(payloads, flags)
-    return [
-        UploadHashes(md5_base64=_b64(md5[i].tobytes()) if want_md5 else "", sha256_base64=_b64(sha[i].tobytes()))
-        for i in range(len(payloads))
-    ]
+    return _UploadHashesView(sha, md5, len(payloads))

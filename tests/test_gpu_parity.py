@@ -222,3 +222,50 @@ def test_chain_and_lane_kernels_agree(ctx, monkeypatch):
         st.close()
     finally:
         c2.close()
+
+
+def test_offsets_beyond_4gib_and_million_small_messages(ctx):
+    """64-bit offsets (messages placed past the 4 GiB mark of one device buffer) and a 10^6-message batch of
+    tiny ragged messages; checked through size-independent properties plus sampled oracle digests."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    total = (4 << 30) + (64 << 20)
+    data = torch.empty(total, dtype=torch.uint8, device=dev)
+    ctx.fill_synth_device(data.data_ptr(), total, seed=91)
+    # (1) the same 3 MiB of bytes hashed at a low and at a > 4 GiB offset must agree with the oracle on both
+    lo, hi = 1 << 20, (4 << 30) + (1 << 20) + 8
+    sizes = np.array([0, 1, 63, 64, 65, 4097, 70001, 1 << 20], np.int64)
+    offs = np.concatenate([lo + np.cumsum(sizes) - sizes, hi + np.cumsum(sizes) - sizes]).astype(np.int64)
+    lens = np.concatenate([sizes, sizes]).astype(np.int64)
+    n = len(lens)
+    off_t, len_t = torch.from_numpy(offs).to(dev), torch.from_numpy(lens).to(dev)
+    sha = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    md5 = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    ctx.hash_batch_device(data.data_ptr(), off_t.data_ptr(), len_t.data_ptr(), n, BOTH, sha.data_ptr(), md5.data_ptr())
+    torch.cuda.synchronize()
+    sha_h, md5_h = sha.cpu().numpy(), md5.cpu().numpy()
+    for i in range(n):
+        msg = synth_bytes(91, int(lens[i]), start=int(offs[i]))
+        assert sha_h[i].tobytes() == c_oracle.sha256(msg) and md5_h[i].tobytes() == c_oracle.md5(msg), i
+    # (2) 10^6 ragged tiny messages (0..255 bytes): every digest of an equal-content message must be equal,
+    #     and a sample must match the oracle
+    m = 1_000_000
+    rng = np.random.default_rng(4)
+    lens2 = rng.integers(0, 256, m).astype(np.int64)
+    offs2 = (np.arange(m, dtype=np.int64) * 256) % (1 << 20)  # messages alias a 1 MiB window: many duplicates
+    off_t, len_t = torch.from_numpy(offs2).to(dev), torch.from_numpy(lens2).to(dev)
+    sha = torch.empty((m, 32), dtype=torch.uint8, device=dev)
+    md5 = torch.empty((m, 16), dtype=torch.uint8, device=dev)
+    ctx.hash_batch_device(data.data_ptr(), off_t.data_ptr(), len_t.data_ptr(), m, BOTH, sha.data_ptr(), md5.data_ptr())
+    torch.cuda.synchronize()
+    sha_h, md5_h = sha.cpu().numpy(), md5.cpu().numpy()
+    key = offs2 * 256 + lens2
+    order = np.argsort(key, kind="stable")
+    same = key[order][1:] == key[order][:-1]
+    assert same.sum() > 100_000
+    assert np.array_equal(sha_h[order][1:][same], sha_h[order][:-1][same])
+    assert np.array_equal(md5_h[order][1:][same], md5_h[order][:-1][same])
+    for i in rng.integers(0, m, 300):
+        msg = synth_bytes(91, int(lens2[i]), start=int(offs2[i]))
+        assert sha_h[i].tobytes() == c_oracle.sha256(msg) and md5_h[i].tobytes() == c_oracle.md5(msg)
