@@ -50,3 +50,48 @@ except Exception:
         function_id: str = ""
         inputs: list = dataclasses.field(default_factory=list)
         function_call_id: str = ""
+
+
+try:  # pragma: no cover
+    from modal_proto.api_pb2 import (  # type: ignore
+        MountFile, MountPutFileRequest, VolumePutFiles2Request, VolumePutFilesRequest)
+except Exception:
+
+    @dataclasses.dataclass
+    class MountPutFileRequest:  # type: ignore[no-redef]  (api.proto:2607-2614)
+        sha256_hex: str = ""
+        data: bytes | None = None
+        data_blob_id: str | None = None
+
+        def WhichOneof(self, _name: str):
+            return "data" if self.data is not None else ("data_blob_id" if self.data_blob_id else None)
+
+    @dataclasses.dataclass
+    class MountFile:  # type: ignore[no-redef]  (api.proto:2582-2587)
+        filename: str = ""
+        sha256_hex: str = ""
+        mode: int = 0
+
+    @dataclasses.dataclass
+    class VolumePutFilesRequest:  # type: ignore[no-redef]
+        volume_id: str = ""
+        files: list = dataclasses.field(default_factory=list)
+        disallow_overwrite_existing_files: bool = False
+
+    class VolumePutFiles2Request:  # type: ignore[no-redef]  (api.proto:3954-3981)
+        @dataclasses.dataclass
+        class Block:
+            contents_sha256: bytes = b""
+            put_response: bytes | None = None
+
+        @dataclasses.dataclass
+        class File:
+            path: str = ""
+            mode: int = 0
+            size: int = 0
+            blocks: list = dataclasses.field(default_factory=list)
+
+        def __init__(self, volume_id="", files=None, disallow_overwrite_existing_files=False):
+            self.volume_id = volume_id
+            self.files = files or []
+            self.disallow_overwrite_existing_files = disallow_overwrite_existing_files
