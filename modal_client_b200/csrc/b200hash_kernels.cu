@@ -5,13 +5,15 @@
 // kernels.  See DESIGN.md for the data layout and the roofline of each kernel.
 //
 //   lane_hash_kernel   one message per lane; fused SHA-256 + MD5 over a single read of the bytes.
-//                      Each lane pulls its own message through shared memory with 1-D TMA bulk
-//                      copies (cp.async.bulk -> UBLKCP) tracked by a per-warp mbarrier ring, reads
-//                      its slot back with conflict-free 128-bit LDS and runs both compression
-//                      functions interleaved in registers.  Bound: INT32 issue (alu+fma pipes).
+//                      Persistent warps pull messages from a device-side work queue and time-slice them
+//                      (32-block quanta) so n messages share the resident lanes evenly.  Each lane gathers
+//                      its own 128-byte chunks with cp.async (LDGSTS) into a private, conflict-free
+//                      shared-memory slot, double buffered, and runs both compression functions interleaved
+//                      in registers.  Bound: INT32 issue (ALU pipe for SHF/LOP3/PRMT, FMA pipe for the adds).
+//   chain_hash_kernel  opt-in (B200H_CHAIN): CTA per long message, TMA bulk tiles (UBLKCP) + mbarrier ring,
+//                      32-lane schedule expansion, SHA and MD5 chains on separate warps.
 //   trim_kernel        warp per message reverse scan for the last non-zero byte (HBM bound).
-//   plan kernels       bucket messages by block count (longest first) so lanes of a warp run
-//                      the same trip count.
+//   plan kernels       bucket messages by block count (longest first) straight into the work queue.
 //   fill_synth_kernel  counter-based synthetic bytes (bench/test data; same stream as synth.py).
 #include "b200hash_kernels.cuh"
 
