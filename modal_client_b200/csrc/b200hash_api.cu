@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <immintrin.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -220,6 +222,34 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     return 0;
 }
 
+// memcpy into the pinned staging ring with non-temporal stores: the destination is written once and then
+// read only by the DMA engine, so bypassing the cache saves the read-for-ownership traffic of a plain
+// memcpy (3 -> 2 memory transfers per byte) and keeps the packer threads from evicting each other.
+static inline void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+#if defined(__AVX2__)
+    if (n >= 4096) {
+        const size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+        memcpy(dst, src, head);
+        dst += head; src += head; n -= head;
+        size_t i = 0;
+        for (; i + 128 <= n; i += 128) {
+            const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+            const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+            const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+            const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+        }
+        _mm_sfence();
+        memcpy(dst + i, src + i, n - i);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
+
 // Copy the packed byte range [lo, hi) of a staged wave into dst (= pinned slot, dst[0] <-> packed byte lo).
 // doff[] are the packed offsets (ascending) of messages i0..i1 inside the wave.
 void pack_range(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint64_t* doff, uint64_t i0,
@@ -233,7 +263,7 @@ void pack_range(const uint8_t* base, const uint64_t* off, const uint64_t* len, c
     }
     for (uint64_t i = a; i < i1 && doff[i] < hi; ++i) {
         const uint64_t s = std::max(doff[i], lo), e = std::min(doff[i] + len[i], hi);
-        if (e > s) memcpy(dst + (s - lo), base + off[i] + (s - doff[i]), (size_t)(e - s));
+        if (e > s) stream_copy(dst + (s - lo), base + off[i] + (s - doff[i]), (size_t)(e - s));
     }
 }
 
