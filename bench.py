@@ -290,7 +290,9 @@ def run_gpu(args) -> None:
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "lane_hash_kernel<sha256,md5>",
                          "kernel_avg_ms": round(kern_avg_ms, 4), "kernel_launches_timed": kern_n,
-                         "note": "SHA-256+MD5 is INT32-issue bound (~27 instr/byte); see DESIGN.md for the ALU roofline"},
+                         "int_alu_peak": 1018.0, "int_alu_frac": round(achieved / 1018.0, 4) if achieved else None,
+                         "note": "hbm frac per the contract; the binding limit is INT32 issue: 1168 ALU-pipe instr per "
+                                 "64 B block at 0.5 warp-instr/clk/SMSP x 592 SMSP x 1.965 GHz = 1018 GB/s (DESIGN.md 5.1)"},
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_value, 3), "unit": "GiB/s", "h2d_bytes_per_step": total_bytes + 16 * N_MSG,
                     "d2h_bytes_per_step": 56 * N_MSG, "steps": e2e_steps,
