@@ -34,6 +34,7 @@ extern "C" {
 #define B200H_E_CUDA (-2)    /* CUDA runtime / driver error (no device, launch failure, ...) */
 #define B200H_E_NOMEM (-3)   /* host or device allocation failed */
 #define B200H_E_STATE (-4)   /* object used in the wrong state (e.g. update after final) */
+#define B200H_E_IO (-5)      /* a file could not be opened / read (b200h_stat_files, b200h_hash_files) */
 
 typedef struct b200h_ctx b200h_ctx;
 typedef struct b200h_stream b200h_stream;
@@ -85,6 +86,22 @@ int b200h_hash_batch_device(b200h_ctx* ctx, const void* d_base, const uint64_t* 
 int b200h_hash_fixed_parts(b200h_ctx* ctx, const uint8_t* base, uint64_t len, uint64_t part_len, uint32_t flags,
                            uint8_t* sha256_out, uint8_t* md5_out, uint64_t* trimmed_len_out,
                            uint8_t etag_md5_out[16], uint64_t* nparts_out);
+
+/* ---- files (native reader pool; no Python I/O, no mmap) ------------------------------------------ */
+
+/* Sizes (and permission bits, may be NULL) of n regular files, stat'ed by the library's I/O threads.
+ * Replaces the per-file seek-to-end / os.stat of _get_file_upload_spec (blob_utils.py:455-457,494). */
+int b200h_stat_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, uint64_t* sizes_out, uint32_t* modes_out);
+
+/* Hash the contents of n files.  The library's reader threads pread() them straight into the pinned staging
+ * ring; waves are hashed while the next ones are being read.  sizes[] = what b200h_stat_files returned (a file
+ * that turns out shorter is B200H_E_IO).
+ *   part_len == 0: one message per file -> n rows (get_file_upload_spec_from_path over a tree:
+ *                  py/modal/volume.py:1209-1216, py/modal/mount.py:467-485, blob_utils.py:490-501)
+ *   part_len  > 0: every file is split into ceil(size/part_len) parts, rows flattened file-major; with
+ *                  B200H_TRIM_ZEROS these are the volumefs2 blocks (blob_utils.py:622-645). */
+int b200h_hash_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, const uint64_t* sizes, uint64_t part_len,
+                     uint32_t flags, uint8_t* sha256_out, uint8_t* md5_out, uint64_t* trimmed_len_out);
 
 /* ---- streaming single message (hashlib-object shaped) ------------------------------------------- */
 

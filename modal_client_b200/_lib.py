@@ -26,7 +26,7 @@ TRIM_ZEROS = 4
 ABI_SYMBOLS = (
     "b200h_create", "b200h_destroy", "b200h_last_error", "b200h_version", "b200h_device_count",
     "b200h_host_alloc", "b200h_host_free", "b200h_hash_batch_host", "b200h_hash_batch_device",
-    "b200h_hash_fixed_parts", "b200h_stream_new", "b200h_stream_update", "b200h_stream_digest",
+    "b200h_hash_fixed_parts", "b200h_stat_files", "b200h_hash_files", "b200h_stream_new", "b200h_stream_update", "b200h_stream_digest",
     "b200h_stream_reset", "b200h_stream_free", "b200h_fill_synth_device", "b200h_launch_count",
     "b200h_profile_enable", "b200h_profile_read",
 )
@@ -87,6 +87,10 @@ def load_library() -> ctypes.CDLL:
         L.b200h_hash_batch_device.restype = i32
         L.b200h_hash_fixed_parts.argtypes = [vp, vp, u64, u64, u32, vp, vp, vp, vp, ctypes.POINTER(u64)]
         L.b200h_hash_fixed_parts.restype = i32
+        L.b200h_stat_files.argtypes = [vp, vp, u64, vp, vp]
+        L.b200h_stat_files.restype = i32
+        L.b200h_hash_files.argtypes = [vp, vp, u64, vp, u64, u32, vp, vp, vp]
+        L.b200h_hash_files.restype = i32
         L.b200h_stream_new.argtypes = [vp, u32, ctypes.POINTER(vp)]
         L.b200h_stream_new.restype = i32
         L.b200h_stream_update.argtypes = [vp, vp, u64]
@@ -250,6 +254,35 @@ class Context:
         self._check(rc, "b200h_hash_fixed_parts")
         assert got.value == nparts
         return sha, md5, trimmed, (etag.tobytes() if want_etag else None)
+
+    # -- files: stat + read + hash entirely inside the library (native reader threads, no mmap / Python I/O)
+    @staticmethod
+    def _c_paths(paths):
+        enc = [os.fsencode(p) for p in paths]
+        return enc, (ctypes.c_char_p * len(enc))(*enc)
+
+    def stat_files(self, paths) -> tuple[np.ndarray, np.ndarray]:
+        """-> (sizes uint64[n], permission bits uint32[n]); raises for missing / non-regular files."""
+        keep, arr = self._c_paths(paths)
+        n = len(keep)
+        sizes, modes = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+        self._check(self._L.b200h_stat_files(self._h, arr, n, _np_ptr(sizes), _np_ptr(modes)), "b200h_stat_files")
+        return sizes, modes
+
+    def hash_files(self, paths, sizes, part_len: int = 0, flags: int = SHA256 | MD5):
+        """-> (sha[rows,32]|None, md5[rows,16]|None, trimmed[rows]); rows = n files (part_len 0) or the
+        file-major list of ceil(size/part_len) parts."""
+        keep, arr = self._c_paths(paths)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+        n = len(keep)
+        rows = n if part_len == 0 else int(((sizes + np.uint64(part_len - 1)) // np.uint64(part_len)).sum())
+        sha = np.empty((rows, 32), np.uint8) if flags & SHA256 else None
+        md5 = np.empty((rows, 16), np.uint8) if flags & MD5 else None
+        trimmed = np.empty(rows, np.uint64)
+        rc = self._L.b200h_hash_files(self._h, arr, n, _np_ptr(sizes), part_len, flags, _np_ptr(sha), _np_ptr(md5),
+                                      _np_ptr(trimmed))
+        self._check(rc, "b200h_hash_files")
+        return sha, md5, trimmed
 
     def fill_synth_device(self, d_ptr: int, nbytes: int, seed: int, start: int = 0, stream: int = 0):
         self._check(self._L.b200h_fill_synth_device(self._h, d_ptr, nbytes, seed, start, stream or None),

@@ -492,74 +492,60 @@ def get_file_upload_spec_from_fileobj(fp: BinaryIO, mount_filename: PurePosixPat
 
 def get_file_upload_specs(
     files: Sequence[tuple[Path, PurePosixPath, int | None]],
+    cache_small_content: bool | None = None,
 ) -> list[FileUploadSpec]:
     """Batched ``get_file_upload_spec_from_path``: every file of a ``Volume.batch_upload`` / ``Mount`` goes
     to the GPU in one batch (the reference fans the per-file hashlib loops over a ThreadPoolExecutor,
-    py/modal/volume.py:1209-1216, py/modal/mount.py:467-485).  Files are mapped read-only, so the bytes
-    travel page cache -> pinned staging -> HBM once; nothing is read through Python.
-    Same size classes / placeholder-MD5 / content caching as ``_get_file_upload_spec``."""
+    py/modal/volume.py:1209-1216, py/modal/mount.py:467-485).  Sizes/modes come from ``b200h_stat_files`` and
+    the bytes are read by the library's native reader threads straight into its pinned staging ring
+    (``b200h_hash_files``): no per-file Python I/O, no mmap.
+    Same size classes / placeholder MD5 as ``_get_file_upload_spec``.  ``content`` (the reference's
+    "avoid the double read" cache for files < 256 KiB) is filled when ``cache_small_content`` is true;
+    the default (None) does so only for batches of <= 4096 files -- for a million-file tree the extra
+    Python read per file would cost more than the hashing."""
     if not files:
         return []
     ctx = get_context()
-    maps: list[mmap.mmap | None] = []
-    views: list[np.ndarray] = []
-    handles = []
-    sizes: list[int] = []
-    try:
-        for filename, _, _ in files:
-            f = open(filename, "rb")
-            handles.append(f)
-            size = os.fstat(f.fileno()).st_size
-            sizes.append(size)
-            if size:
-                mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
-                maps.append(mm)
-                views.append(np.frombuffer(mm, dtype=np.uint8))
-            else:
-                maps.append(None)
-                views.append(np.zeros(0, np.uint8))
-        classes = [_size_class(s) for s in sizes]
-        # one fused SHA-256+MD5 batch for the files that need both, a SHA-only batch for the > 1 GiB class
-        both = [i for i, c in enumerate(classes) if c[1]]
-        sha_only = [i for i, c in enumerate(classes) if not c[1]]
-        sha_of: dict[int, bytes] = {}
-        md5_of: dict[int, bytes] = {}
-        if both:
-            sha, md5, _ = ctx.hash_buffers([views[i] for i in both], _lib.SHA256 | _lib.MD5)
-            for k, i in enumerate(both):
-                sha_of[i], md5_of[i] = sha[k].tobytes(), md5[k].tobytes()
-        if sha_only:
-            sha, _, _ = ctx.hash_buffers([views[i] for i in sha_only], _lib.SHA256)
-            for k, i in enumerate(sha_only):
-                sha_of[i] = sha[k].tobytes()
-        specs = []
-        for i, (filename, mount_filename, mode) in enumerate(files):
-            use_blob, want_md5, cache = classes[i]
-            specs.append(
-                FileUploadSpec(
-                    source=(lambda fn=filename: open(fn, "rb")),
-                    source_description=filename,
-                    source_is_path=isinstance(filename, Path),
-                    mount_filename=PurePosixPath(mount_filename).as_posix(),
-                    use_blob=use_blob,
-                    sha256_hex=sha_of[i].hex(),
-                    md5_hex=md5_of[i].hex() if want_md5 else _MD5_PLACEHOLDER,
-                    mode=(mode or _default_mode(Path(filename))) & 0o7777,
-                    size=sizes[i],
-                    content=views[i].tobytes() if cache else None,
-                )
+    paths = [str(f[0]) for f in files]
+    sizes, modes = ctx.stat_files(paths)
+    classes = [_size_class(int(s)) for s in sizes]
+    # one fused SHA-256+MD5 batch for the files that need both, a SHA-only batch for the > 1 GiB class
+    both = [i for i, c in enumerate(classes) if c[1]]
+    sha_only = [i for i, c in enumerate(classes) if not c[1]]
+    sha_of: dict[int, bytes] = {}
+    md5_of: dict[int, bytes] = {}
+    if both:
+        sha, md5, _ = ctx.hash_files([paths[i] for i in both], sizes[both], 0, _lib.SHA256 | _lib.MD5)
+        for k, i in enumerate(both):
+            sha_of[i], md5_of[i] = sha[k].tobytes(), md5[k].tobytes()
+    if sha_only:
+        sha, _, _ = ctx.hash_files([paths[i] for i in sha_only], sizes[sha_only], 0, _lib.SHA256)
+        for k, i in enumerate(sha_only):
+            sha_of[i] = sha[k].tobytes()
+    if cache_small_content is None:
+        cache_small_content = len(files) <= 4096
+    specs = []
+    for i, (filename, mount_filename, mode) in enumerate(files):
+        use_blob, want_md5, cache = classes[i]
+        content = None
+        if cache and cache_small_content:
+            with open(filename, "rb") as f:
+                content = f.read()
+        specs.append(
+            FileUploadSpec(
+                source=(lambda fn=filename: open(fn, "rb")),
+                source_description=filename,
+                source_is_path=isinstance(filename, Path),
+                mount_filename=PurePosixPath(mount_filename).as_posix(),
+                use_blob=use_blob,
+                sha256_hex=sha_of[i].hex(),
+                md5_hex=md5_of[i].hex() if want_md5 else _MD5_PLACEHOLDER,
+                mode=(mode if mode else int(modes[i])) & 0o7777,
+                size=int(sizes[i]),
+                content=content,
             )
-        return specs
-    finally:
-        views.clear()
-        for mm in maps:
-            if mm is not None:
-                try:
-                    mm.close()
-                except BufferError:
-                    pass
-        for f in handles:
-            f.close()
+        )
+    return specs
 
 
 # ---------------------------------------------------------------------------- FileUploadSpec2 (v2)
@@ -696,61 +682,34 @@ async def file_upload_specs2(
     files: Sequence[tuple[Path, PurePosixPath, int | None]],
 ) -> list[FileUploadSpec2]:
     """Batched ``FileUploadSpec2.from_path`` for a whole ``batch_upload``: the blocks of ALL files form one
-    GPU batch (so a tree of many small files is as efficient as one big file)."""
+    GPU batch (so a tree of many small files is as efficient as one big file), read by the library's native
+    reader threads (``b200h_hash_files`` with part_len = BLOCK_SIZE and zero trimming)."""
     if not files:
         return []
 
     def run() -> list[FileUploadSpec2]:
         ctx = get_context()
-        handles, maps, views, sizes = [], [], [], []
-        try:
-            for filename, _, _ in files:
-                f = open(filename, "rb")
-                handles.append(f)
-                size = os.fstat(f.fileno()).st_size
-                sizes.append(size)
-                if size:
-                    mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
-                    maps.append(mm)
-                    views.append(np.frombuffer(mm, dtype=np.uint8))
-                else:
-                    maps.append(None)
-                    views.append(np.zeros(0, np.uint8))
-            # one message per block, addressed absolutely (base=None)
-            owner, addr, length = [], [], []
-            for i, v in enumerate(views):
-                for start in range(0, sizes[i], BLOCK_SIZE):
-                    owner.append(i)
-                    addr.append(v.ctypes.data + start)
-                    length.append(min(BLOCK_SIZE, sizes[i] - start))
-            per_file: list[list[FileUploadBlock]] = [[] for _ in files]
-            if owner:
-                sha, _, trimmed = ctx.hash_batch_host(None, np.array(addr, np.uint64), np.array(length, np.uint64),
-                                                      _lib.SHA256 | _lib.TRIM_ZEROS)
-                for k, i in enumerate(owner):
-                    start = len(per_file[i]) * BLOCK_SIZE
-                    per_file[i].append(FileUploadBlock(start, start + int(trimmed[k]), sha[k].tobytes()))
-            return [
+        paths = [str(f[0]) for f in files]
+        sizes, modes = ctx.stat_files(paths)
+        sha, _, trimmed = ctx.hash_files(paths, sizes, BLOCK_SIZE, _lib.SHA256 | _lib.TRIM_ZEROS)
+        out, row = [], 0
+        for i, (filename, mount_filename, mode) in enumerate(files):
+            size = int(sizes[i])
+            blocks = []
+            for start in range(0, size, BLOCK_SIZE):
+                blocks.append(FileUploadBlock(start, start + int(trimmed[row]), sha[row].tobytes()))
+                row += 1
+            out.append(
                 FileUploadSpec2(
                     source=(lambda fn=filename: open(fn, "rb")),
                     source_description=filename,
                     path=PurePosixPath(mount_filename).as_posix(),
-                    blocks=per_file[i],
-                    mode=(mode or _default_mode(Path(filename))) & 0o7777,
-                    size=sizes[i],
+                    blocks=blocks,
+                    mode=(mode if mode else int(modes[i])) & 0o7777,
+                    size=size,
                 )
-                for i, (filename, mount_filename, mode) in enumerate(files)
-            ]
-        finally:
-            views.clear()
-            for mm in maps:
-                if mm is not None:
-                    try:
-                        mm.close()
-                    except BufferError:
-                        pass
-            for f in handles:
-                f.close()
+            )
+        return out
 
     return await asyncio.to_thread(run)
 

@@ -7,9 +7,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <fcntl.h>
 #include <immintrin.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -71,6 +76,7 @@ struct b200h_ctx {
     double prof_ms = 0.0;
     uint64_t prof_n = 0;
     int pack_threads = 1;
+    int io_threads = 1;
 };
 
 struct b200h_stream {
@@ -252,8 +258,21 @@ static inline void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) {
 
 // Copy the packed byte range [lo, hi) of a staged wave into dst (= pinned slot, dst[0] <-> packed byte lo).
 // doff[] are the packed offsets (ascending) of messages i0..i1 inside the wave.
-void pack_range(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint64_t* doff, uint64_t i0,
-                uint64_t i1, uint64_t lo, uint64_t hi, uint8_t* dst) {
+// Where the bytes of message i come from: host memory (base + off[i]) or a file (paths[file_of[i]] at byte
+// offset off[i]).  File reads go straight into the pinned staging ring with pread -- no intermediate copy.
+struct Source {
+    const uint8_t* base = nullptr;
+    const uint64_t* off = nullptr;
+    const char* const* paths = nullptr;
+    const uint64_t* file_of = nullptr;
+    std::atomic<int>* io_errno = nullptr;  // first I/O failure (errno, or -1 for a short read)
+    std::atomic<uint64_t>* io_file = nullptr;
+};
+
+// Copy the packed byte range [lo, hi) of a staged wave into dst (= pinned slot, dst[0] <-> packed byte lo).
+// doff[] are the packed offsets (ascending) of messages i0..i1 inside the wave.
+void pack_range(const Source& src, const uint64_t* len, const uint64_t* doff, uint64_t i0, uint64_t i1, uint64_t lo,
+                uint64_t hi, uint8_t* dst) {
     // first message whose packed end is beyond lo
     uint64_t a = i0, b = i1;
     while (a < b) {
@@ -261,32 +280,78 @@ void pack_range(const uint8_t* base, const uint64_t* off, const uint64_t* len, c
         if (doff[m] + len[m] <= lo) a = m + 1;
         else b = m;
     }
+    int fd = -1;
+    uint64_t fd_file = ~0ull;
     for (uint64_t i = a; i < i1 && doff[i] < hi; ++i) {
         const uint64_t s = std::max(doff[i], lo), e = std::min(doff[i] + len[i], hi);
-        if (e > s) stream_copy(dst + (s - lo), base + off[i] + (s - doff[i]), (size_t)(e - s));
+        if (e <= s) continue;
+        if (!src.paths) {
+            stream_copy(dst + (s - lo), src.base + src.off[i] + (s - doff[i]), (size_t)(e - s));
+            continue;
+        }
+        if (src.io_errno->load(std::memory_order_relaxed)) break;
+        const uint64_t f = src.file_of[i];
+        if (f != fd_file) {
+            if (fd >= 0) close(fd);
+            fd = open(src.paths[f], O_RDONLY | O_CLOEXEC);
+            fd_file = f;
+        }
+        int err = fd < 0 ? errno : 0;
+        uint64_t got = 0;
+        const uint64_t want = e - s, at = src.off[i] + (s - doff[i]);
+        while (!err && got < want) {
+            const ssize_t r = pread(fd, dst + (s - lo) + got, (size_t)(want - got), (off_t)(at + got));
+            if (r < 0) {
+                if (errno == EINTR) continue;
+                err = errno;
+            } else if (r == 0) {
+                err = -1;  // the file is shorter than the size the caller passed
+            } else {
+                got += (uint64_t)r;
+            }
+        }
+        if (err) {
+            int expected = 0;
+            if (src.io_errno->compare_exchange_strong(expected, err)) src.io_file->store(f);
+            break;
+        }
     }
+    if (fd >= 0) close(fd);
 }
 
-void pack_parallel(int threads, const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint64_t* doff,
-                   uint64_t i0, uint64_t i1, uint64_t lo, uint64_t hi, uint8_t* dst) {
+void pack_parallel(int threads, const Source& src, const uint64_t* len, const uint64_t* doff, uint64_t i0, uint64_t i1,
+                   uint64_t lo, uint64_t hi, uint8_t* dst) {
     const uint64_t bytes = hi - lo;
-    int t = (int)std::min<uint64_t>((uint64_t)threads, bytes / (4u << 20));
+    // memory sources: one thread per >= 4 MiB; file sources: syscalls dominate small files, so also split by count
+    uint64_t want = bytes / (4u << 20);
+    if (src.paths) want = std::max<uint64_t>(want, (i1 - i0) / 64);
+    const int t = (int)std::min<uint64_t>((uint64_t)threads, want);
     if (t <= 1) {
-        pack_range(base, off, len, doff, i0, i1, lo, hi, dst);
+        pack_range(src, len, doff, i0, i1, lo, hi, dst);
         return;
     }
     std::vector<std::thread> th;
     th.reserve(t);
     for (int k = 0; k < t; ++k) {
         const uint64_t a = lo + bytes * k / t, b = lo + bytes * (k + 1) / t;
-        th.emplace_back([=] { pack_range(base, off, len, doff, i0, i1, a, b, dst + (a - lo)); });
+        th.emplace_back([=, &src] { pack_range(src, len, doff, i0, i1, a, b, dst + (a - lo)); });
     }
     for (auto& x : th) x.join();
 }
 
 int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n,
-                         uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, uint64_t* trim_out, uint8_t* etag_out) {
+                         uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, uint64_t* trim_out, uint8_t* etag_out,
+                         const char* const* paths = nullptr, const uint64_t* file_of = nullptr) {
     if (n == 0) return 0;
+    std::atomic<int> io_errno{0};
+    std::atomic<uint64_t> io_file{0};
+    Source src;
+    src.base = base;
+    src.off = off;
+    src.paths = paths;
+    src.file_of = file_of;
+    src.io_errno = &io_errno;
+    src.io_file = &io_file;
     if (!off || !len) return fail(ctx, B200H_E_INVALID, "offsets/lengths must not be NULL");
     if (!(flags & (B200H_SHA256 | B200H_MD5))) return fail(ctx, B200H_E_INVALID, "flags select neither SHA256 nor MD5");
     if (etag_out && !(flags & B200H_MD5)) return fail(ctx, B200H_E_INVALID, "etag requires B200H_MD5");
@@ -294,7 +359,7 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
 
     // Page-locked source?  Then DMA straight from the caller's memory, no staging copy.
     bool direct = false;
-    if (base) {
+    if (base && !paths) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, base) == cudaSuccess) direct = (at.type == cudaMemoryTypeHost);
         else cudaGetLastError();
@@ -375,7 +440,15 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
             for (uint64_t lo = 0; lo < w.bytes; lo += ctx->pin_cap) {
                 const uint64_t hi = std::min<uint64_t>(w.bytes, lo + ctx->pin_cap);
                 if (pin_used[pin_slot]) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_pin[pin_slot]));
-                pack_parallel(ctx->pack_threads, base, off, len, doff, w.i0, w.i1, lo, hi, ctx->pin[pin_slot]);
+                pack_parallel(paths ? ctx->io_threads : ctx->pack_threads, src, len, doff, w.i0, w.i1, lo, hi,
+                              ctx->pin[pin_slot]);
+                if (io_errno.load()) {
+                    const int e = io_errno.load();
+                    CU_TRY(ctx, cudaDeviceSynchronize());
+                    return fail(ctx, B200H_E_IO,
+                                std::string("reading ") + paths[io_file.load()] + ": " +
+                                    (e == -1 ? "file is shorter than the size passed in" : strerror(e)));
+                }
                 CU_TRY(ctx, cudaMemcpyAsync(ctx->dwave[slot] + lo, ctx->pin[pin_slot], hi - lo, cudaMemcpyHostToDevice,
                                             ctx->s_copy));
                 CU_TRY(ctx, cudaEventRecord(ctx->ev_pin[pin_slot], ctx->s_copy));
@@ -496,6 +569,8 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
     unsigned hc = std::thread::hardware_concurrency();
     ctx->pack_threads = (int)std::min(16u, std::max(1u, hc / 2));  // measured best on 2x Xeon 8562Y+ (8..64 tried)
     if (const char* e = getenv("B200H_PACK_THREADS")) ctx->pack_threads = std::max(1, atoi(e));
+    ctx->io_threads = (int)std::min(64u, std::max(1u, hc));  // file reads are syscall/latency bound: more threads
+    if (const char* e = getenv("B200H_IO_THREADS")) ctx->io_threads = std::max(1, atoi(e));
 #undef CU_INIT
     *out = ctx;
     return 0;
@@ -596,6 +671,63 @@ int b200h_hash_fixed_parts(b200h_ctx* ctx, const uint8_t* base, uint64_t len, ui
     }
     return hash_batch_host_impl(ctx, base, off.data(), ln.data(), nparts, flags & 7u, sha256_out, md5_out,
                                 trimmed_len_out, etag_md5_out);
+}
+
+// ---------------------------------------------------------------------------------------------- files
+
+int b200h_stat_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, uint64_t* sizes_out, uint32_t* modes_out) {
+    if (!ctx) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n && (!paths || !sizes_out)) return fail(ctx, B200H_E_INVALID, "paths/sizes_out must not be NULL");
+    std::atomic<int> err{0};
+    std::atomic<uint64_t> bad{0};
+    const int t = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->io_threads, n / 256));
+    auto work = [&](uint64_t a, uint64_t b) {
+        for (uint64_t i = a; i < b && !err.load(std::memory_order_relaxed); ++i) {
+            struct stat sb;
+            if (stat(paths[i], &sb) != 0 || !S_ISREG(sb.st_mode)) {
+                int expected = 0;
+                if (err.compare_exchange_strong(expected, errno ? errno : EINVAL)) bad.store(i);
+                return;
+            }
+            sizes_out[i] = (uint64_t)sb.st_size;
+            if (modes_out) modes_out[i] = (uint32_t)(sb.st_mode & 07777);
+        }
+    };
+    if (t <= 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < t; ++k) th.emplace_back(work, n * k / t, n * (k + 1) / t);
+        for (auto& x : th) x.join();
+    }
+    if (err.load()) return fail(ctx, B200H_E_IO, std::string("stat ") + paths[bad.load()] + ": " + strerror(err.load()));
+    return 0;
+}
+
+int b200h_hash_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, const uint64_t* sizes, uint64_t part_len,
+                     uint32_t flags, uint8_t* sha256_out, uint8_t* md5_out, uint64_t* trimmed_len_out) {
+    if (!ctx) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n && (!paths || !sizes)) return fail(ctx, B200H_E_INVALID, "paths/sizes must not be NULL");
+    // message list: one per file (part_len == 0) or one per part_len-sized part, file-major
+    std::vector<uint64_t> off, len, file_of;
+    for (uint64_t f = 0; f < n; ++f) {
+        if (part_len == 0) {
+            off.push_back(0);
+            len.push_back(sizes[f]);
+            file_of.push_back(f);
+        } else {
+            for (uint64_t o = 0; o < sizes[f]; o += part_len) {
+                off.push_back(o);
+                len.push_back(std::min(part_len, sizes[f] - o));
+                file_of.push_back(f);
+            }
+        }
+    }
+    if (off.empty()) return 0;
+    return hash_batch_host_impl(ctx, nullptr, off.data(), len.data(), off.size(), flags & 7u, sha256_out, md5_out,
+                                trimmed_len_out, nullptr, paths, file_of.data());
 }
 
 // ------------------------------------------------------------------------------------------ streaming

@@ -82,3 +82,36 @@ class FakeContext:
 
     def stream(self, flags=_lib.SHA256 | _lib.MD5):
         return FakeStream(flags)
+
+    def stat_files(self, paths):
+        import os
+
+        st = [os.stat(p) for p in paths]
+        for p, x in zip(paths, st):
+            if not os.path.isfile(p):
+                raise _lib.B200HashError(f"stat {p}: not a regular file")
+        return (np.array([x.st_size for x in st], np.uint64), np.array([x.st_mode & 0o7777 for x in st], np.uint32))
+
+    def hash_files(self, paths, sizes, part_len=0, flags=_lib.SHA256 | _lib.MD5):
+        self.calls.append(("hash_files", len(paths), part_len, flags))
+        shas, md5s, lens = [], [], []
+        for p, size in zip(paths, np.asarray(sizes, np.uint64)):
+            data = np.fromfile(p, dtype=np.uint8)
+            if data.size < int(size):
+                raise _lib.B200HashError(f"reading {p}: file is shorter than the size passed in")
+            data = data[: int(size)]
+            if part_len == 0:
+                starts, ln = np.array([0], np.uint64), np.array([data.size], np.uint64)
+            else:
+                starts = np.arange(0, data.size, part_len, dtype=np.uint64)
+                ln = np.minimum(part_len, data.size - starts).astype(np.uint64)
+            s, m, e = c_oracle.hash_batch(data, starts, ln, sha=bool(flags & _lib.SHA256), md5=bool(flags & _lib.MD5),
+                                          trim=bool(flags & _lib.TRIM_ZEROS))
+            if s is not None:
+                shas.append(s)
+            if m is not None:
+                md5s.append(m)
+            lens.append(e)
+        cat = lambda xs, w: (np.concatenate(xs) if xs else np.zeros((0, w), np.uint8))  # noqa: E731
+        return (cat(shas, 32) if flags & _lib.SHA256 else None, cat(md5s, 16) if flags & _lib.MD5 else None,
+                np.concatenate(lens) if lens else np.zeros(0, np.uint64))

@@ -269,3 +269,34 @@ def test_offsets_beyond_4gib_and_million_small_messages(ctx):
     for i in rng.integers(0, m, 300):
         msg = synth_bytes(91, int(lens2[i]), start=int(offs2[i]))
         assert sha_h[i].tobytes() == c_oracle.sha256(msg) and md5_h[i].tobytes() == c_oracle.md5(msg)
+
+
+def test_native_file_reader_matches_memory_path_and_reports_io_errors(ctx, tmp_path):
+    paths, blobs = [], []
+    for i, n in enumerate([0, 1, 4095, 70_000, 300_001, (1 << 20) + 17]):
+        data = synth_bytes(50 + i, n)
+        p = tmp_path / f"f{i}"
+        p.write_bytes(data)
+        paths.append(str(p))
+        blobs.append(data)
+    sizes, modes = ctx.stat_files(paths)
+    assert sizes.tolist() == [len(b) for b in blobs]
+    sha, md5, trimmed = ctx.hash_files(paths, sizes, 0, BOTH)
+    for b, s, m in zip(blobs, sha, md5):
+        assert s.tobytes() == c_oracle.sha256(b) and m.tobytes() == c_oracle.md5(b)
+    # fixed parts, file-major, trimmed
+    sha, _, trimmed = ctx.hash_files(paths, sizes, 65536, _lib.SHA256 | _lib.TRIM_ZEROS)
+    row = 0
+    for b in blobs:
+        for o in range(0, len(b), 65536):
+            part = b[o : o + 65536].rstrip(b"\0")
+            assert int(trimmed[row]) == len(part) and sha[row].tobytes() == c_oracle.sha256(part)
+            row += 1
+    assert row == len(trimmed)
+    with pytest.raises(_lib.B200HashError, match="nope"):
+        ctx.stat_files(paths + [str(tmp_path / "nope")])
+    (tmp_path / "f3").write_bytes(b"short now")  # shrank after stat
+    with pytest.raises(_lib.B200HashError, match="shorter"):
+        ctx.hash_files(paths, sizes, 0, BOTH)
+    s2, _, _ = ctx.hash_files(paths[:3], sizes[:3], 0, _lib.SHA256)  # the context is still usable
+    assert s2[2].tobytes() == c_oracle.sha256(blobs[2])
