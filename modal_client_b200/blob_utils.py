@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import asyncio
 import dataclasses
+import functools
 import mmap
 import os
 import platform
@@ -506,42 +507,48 @@ def get_file_upload_specs(
     if not files:
         return []
     ctx = get_context()
+    n = len(files)
     paths = [str(f[0]) for f in files]
     sizes, modes = ctx.stat_files(paths)
-    classes = [_size_class(int(s)) for s in sizes]
+    # size classes, vectorised (same comparisons as _size_class)
+    use_blob = sizes >= LARGE_FILE_LIMIT
+    want_md5 = ~(use_blob & (sizes > MULTIPART_UPLOAD_THRESHOLD))
+    cacheable = ~use_blob & (sizes < SMALL_FILE_INLINE_LIMIT)
     # one fused SHA-256+MD5 batch for the files that need both, a SHA-only batch for the > 1 GiB class
-    both = [i for i, c in enumerate(classes) if c[1]]
-    sha_only = [i for i, c in enumerate(classes) if not c[1]]
-    sha_of: dict[int, bytes] = {}
-    md5_of: dict[int, bytes] = {}
-    if both:
-        sha, md5, _ = ctx.hash_files([paths[i] for i in both], sizes[both], 0, _lib.SHA256 | _lib.MD5)
-        for k, i in enumerate(both):
-            sha_of[i], md5_of[i] = sha[k].tobytes(), md5[k].tobytes()
-    if sha_only:
+    sha_all = np.empty((n, 32), np.uint8)
+    md5_all = np.zeros((n, 16), np.uint8)
+    both = np.flatnonzero(want_md5)
+    sha_only = np.flatnonzero(~want_md5)
+    if both.size:
+        sha, md5, _ = ctx.hash_files([paths[i] for i in both] if both.size != n else paths, sizes[both], 0,
+                                     _lib.SHA256 | _lib.MD5)
+        sha_all[both], md5_all[both] = sha, md5
+    if sha_only.size:
         sha, _, _ = ctx.hash_files([paths[i] for i in sha_only], sizes[sha_only], 0, _lib.SHA256)
-        for k, i in enumerate(sha_only):
-            sha_of[i] = sha[k].tobytes()
+        sha_all[sha_only] = sha
+    sha_hex, md5_hex = sha_all.tobytes().hex(), md5_all.tobytes().hex()  # one conversion, sliced per file below
     if cache_small_content is None:
-        cache_small_content = len(files) <= 4096
+        cache_small_content = n <= 4096
+    sizes_l, modes_l = sizes.tolist(), modes.tolist()
+    use_blob_l, want_md5_l, cache_l = use_blob.tolist(), want_md5.tolist(), cacheable.tolist()
     specs = []
     for i, (filename, mount_filename, mode) in enumerate(files):
-        use_blob, want_md5, cache = classes[i]
         content = None
-        if cache and cache_small_content:
+        if cache_small_content and cache_l[i]:
             with open(filename, "rb") as f:
                 content = f.read()
         specs.append(
             FileUploadSpec(
-                source=(lambda fn=filename: open(fn, "rb")),
+                source=functools.partial(open, filename, "rb"),
                 source_description=filename,
                 source_is_path=isinstance(filename, Path),
-                mount_filename=PurePosixPath(mount_filename).as_posix(),
-                use_blob=use_blob,
-                sha256_hex=sha_of[i].hex(),
-                md5_hex=md5_of[i].hex() if want_md5 else _MD5_PLACEHOLDER,
-                mode=(mode if mode else int(modes[i])) & 0o7777,
-                size=int(sizes[i]),
+                mount_filename=mount_filename.as_posix() if isinstance(mount_filename, PurePosixPath)
+                else PurePosixPath(mount_filename).as_posix(),
+                use_blob=use_blob_l[i],
+                sha256_hex=sha_hex[64 * i : 64 * i + 64],
+                md5_hex=md5_hex[32 * i : 32 * i + 32] if want_md5_l[i] else _MD5_PLACEHOLDER,
+                mode=(mode if mode else modes_l[i]) & 0o7777,
+                size=sizes_l[i],
                 content=content,
             )
         )
@@ -693,19 +700,20 @@ async def file_upload_specs2(
         sizes, modes = ctx.stat_files(paths)
         sha, _, trimmed = ctx.hash_files(paths, sizes, BLOCK_SIZE, _lib.SHA256 | _lib.TRIM_ZEROS)
         out, row = [], 0
+        sizes_l, modes_l, trimmed_l, sha_raw = sizes.tolist(), modes.tolist(), trimmed.tolist(), sha.tobytes()
         for i, (filename, mount_filename, mode) in enumerate(files):
-            size = int(sizes[i])
+            size = sizes_l[i]
             blocks = []
             for start in range(0, size, BLOCK_SIZE):
-                blocks.append(FileUploadBlock(start, start + int(trimmed[row]), sha[row].tobytes()))
+                blocks.append(FileUploadBlock(start, start + trimmed_l[row], sha_raw[32 * row : 32 * row + 32]))
                 row += 1
             out.append(
                 FileUploadSpec2(
-                    source=(lambda fn=filename: open(fn, "rb")),
+                    source=functools.partial(open, filename, "rb"),
                     source_description=filename,
                     path=PurePosixPath(mount_filename).as_posix(),
                     blocks=blocks,
-                    mode=(mode if mode else int(modes[i])) & 0o7777,
+                    mode=(mode if mode else modes_l[i]) & 0o7777,
                     size=size,
                 )
             )

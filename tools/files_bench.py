@@ -1,7 +1,7 @@
 """tools/files_bench.py -- Volume.batch_upload spec building over a real directory tree, end to end from files:
 the reference's way (ThreadPoolExecutor over get_file_upload_spec_from_path == oracle/ref_port.file_spec_fields on
 hashlib) vs modal_client_b200.blob_utils.get_file_upload_specs / file_upload_specs2 (native reader -> GPU).
-usage: python tools/files_bench.py [n_files=20000] [total_GiB=2] [dir=/dev/shm|/tmp]"""
+usage: python tools/files_bench.py [n_files=20000] [total_GiB=2] [dir=/dev/shm|/tmp] [sigma=1.5]"""
 import asyncio
 import os
 import shutil
@@ -24,7 +24,8 @@ where = sys.argv[3] if len(sys.argv) > 3 else ("/dev/shm" if os.path.isdir("/dev
 root = Path(tempfile.mkdtemp(prefix="b200h_tree_", dir=where))
 try:
     rng = np.random.default_rng(0)
-    sizes = np.clip(rng.lognormal(np.log(102400) - 1.5**2 / 2, 1.5, n), 1, 1 << 28)
+    sigma = float(sys.argv[4]) if len(sys.argv) > 4 else 1.5
+    sizes = np.clip(rng.lognormal(np.log(102400) - sigma**2 / 2, sigma, n), 1, 1 << 28)
     sizes = np.maximum(1, (sizes * (total * 2**30 / sizes.sum())).astype(np.int64))
     blob = synth_array(9, int(sizes.max()) + (1 << 20))
     files = []
