@@ -569,7 +569,7 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
     unsigned hc = std::thread::hardware_concurrency();
     ctx->pack_threads = (int)std::min(16u, std::max(1u, hc / 2));  // measured best on 2x Xeon 8562Y+ (8..64 tried)
     if (const char* e = getenv("B200H_PACK_THREADS")) ctx->pack_threads = std::max(1, atoi(e));
-    ctx->io_threads = (int)std::min(64u, std::max(1u, hc));  // file reads are syscall/latency bound: more threads
+    ctx->io_threads = (int)std::min(16u, std::max(1u, hc));  // measured: 16 > 32 > 64 > 128 (kernel-side contention)
     if (const char* e = getenv("B200H_IO_THREADS")) ctx->io_threads = std::max(1, atoi(e));
 #undef CU_INIT
     *out = ctx;
