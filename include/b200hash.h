@@ -43,7 +43,8 @@ typedef struct b200h_stream b200h_stream;
 
 /* Bind a context to CUDA device `device`.  pinned_bytes / device_bytes size the host staging ring and
  * the HBM staging buffers used by the *_host entry points (0 = defaults: 512 MiB pinned, 8 GiB HBM,
- * both split in two for double buffering; they grow on demand for a message larger than half). */
+ * both split in two for double buffering).  A message larger than one HBM wave slot is hashed in
+ * consecutive segments with the chaining state kept on the device, so message size is not limited by them. */
 int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx** out);
 void b200h_destroy(b200h_ctx* ctx);
 /* ctx may be NULL: returns the message of the last failed b200h_create on this thread. */

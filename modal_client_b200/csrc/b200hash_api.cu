@@ -29,6 +29,10 @@
 
 using namespace b200h;
 
+static const uint32_t kShaIv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,
+                                   0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+static const uint32_t kMd5Iv[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -42,6 +46,12 @@ struct Wave {
     uint64_t i0, i1;    // message index range [i0, i1)
     uint64_t src_lo;    // direct mode: host offset (relative to base) of the first byte copied
     uint64_t bytes;     // bytes occupying the device wave buffer
+    // A message larger than one wave slot is hashed as consecutive segments of itself (one wave each), the
+    // chaining state travelling through a device-resident ChainState: seg != 0, message i0, bytes
+    // [seg_start, seg_start + bytes) of it.
+    int seg = 0;        // 0 = ordinary wave, 1 = first/middle segment, 2 = last segment
+    bool seg_first = false;
+    uint64_t seg_start = 0;
 };
 
 }  // namespace
@@ -372,15 +382,32 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
 
     // ---- carve the batch into waves that fit one HBM wave slot
     size_t cap = std::max(ctx->dwave_cap, ctx->dwave_want);
+    const uint64_t seg_cap = cap & ~uint64_t(63);
     std::vector<Wave> waves;
     {
         uint64_t i = 0;
         while (i < n) {
             Wave w{i, i, 0, 0};
+            if (len[i] + 16 > cap) {
+                // oversized message: consecutive 64-byte-aligned segments, one wave each
+                if (flags & B200H_TRIM_ZEROS)
+                    return fail(ctx, B200H_E_INVALID, "B200H_TRIM_ZEROS is not supported for a message larger than one staging wave");
+                for (uint64_t s0 = 0; s0 < len[i]; s0 += seg_cap) {
+                    Wave sw{i, i + 1, 0, std::min<uint64_t>(seg_cap, len[i] - s0)};
+                    sw.seg = (s0 + seg_cap >= len[i]) ? 2 : 1;
+                    sw.seg_first = s0 == 0;
+                    sw.seg_start = s0;
+                    waves.push_back(sw);
+                }
+                doff[i] = 0;
+                i += 1;
+                continue;
+            }
             if (direct) {
                 uint64_t lo = off[i], hi = off[i] + len[i];
                 uint64_t j = i + 1;
                 for (; j < n; ++j) {
+                    if (len[j] + 16 > cap) break;  // oversized: gets its own segment waves
                     const uint64_t nlo = std::min(lo, off[j]), nhi = std::max(hi, off[j] + len[j]);
                     if (nhi - (nlo & ~15ull) > cap) break;
                     lo = nlo;
@@ -395,6 +422,7 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
                 uint64_t j = i;
                 for (; j < n; ++j) {
                     const uint64_t need = (len[j] + 15) & ~15ull;
+                    if (len[j] + 16 > cap) break;  // oversized: gets its own segment waves
                     if (j > i && used + need > cap) break;
                     doff[j] = used;
                     used += need;
@@ -426,22 +454,35 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
     CU_TRY(ctx, cudaMemcpyAsync(d_off, doff, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_comp));
     CU_TRY(ctx, cudaMemcpyAsync(d_len, hlen, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_comp));
 
+    if (int rc = ensure_dev(ctx, ctx->d_small, 256)) return rc;
+    uint64_t* d_segmeta = (uint64_t*)((uint8_t*)ctx->d_small.p + 64);
+    ChainState* d_segstate = (ChainState*)((uint8_t*)ctx->d_small.p + 128);
+
     bool pin_used[2] = {false, false};
     int pin_slot = 0;
     for (size_t wi = 0; wi < waves.size(); ++wi) {
         const Wave& w = waves[wi];
         const int slot = (int)(wi & 1);
         if (wi >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_copy, ctx->ev_consumed[slot], 0));
+        // a segment wave is message w.i0 restricted to [seg_start, seg_start + bytes), placed at device offset 0
+        const uint64_t seg_off1 = w.seg ? off[w.i0] + w.seg_start : 0, seg_len1 = w.bytes, seg_doff1 = 0;
+        const uint64_t seg_file1 = (w.seg && file_of) ? file_of[w.i0] : 0;
+        Source seg_src = src;
+        seg_src.off = &seg_off1;
+        seg_src.file_of = file_of ? &seg_file1 : nullptr;
         if (direct) {
-            if (w.bytes)
-                CU_TRY(ctx, cudaMemcpyAsync(ctx->dwave[slot], base + w.src_lo, w.bytes, cudaMemcpyHostToDevice,
-                                            ctx->s_copy));
+            const uint8_t* from = w.seg ? base + off[w.i0] + w.seg_start : base + w.src_lo;
+            if (w.bytes) CU_TRY(ctx, cudaMemcpyAsync(ctx->dwave[slot], from, w.bytes, cudaMemcpyHostToDevice, ctx->s_copy));
         } else {
             for (uint64_t lo = 0; lo < w.bytes; lo += ctx->pin_cap) {
                 const uint64_t hi = std::min<uint64_t>(w.bytes, lo + ctx->pin_cap);
                 if (pin_used[pin_slot]) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_pin[pin_slot]));
-                pack_parallel(paths ? ctx->io_threads : ctx->pack_threads, src, len, doff, w.i0, w.i1, lo, hi,
-                              ctx->pin[pin_slot]);
+                if (w.seg)
+                    pack_parallel(paths ? ctx->io_threads : ctx->pack_threads, seg_src, &seg_len1, &seg_doff1, 0, 1, lo, hi,
+                                  ctx->pin[pin_slot]);
+                else
+                    pack_parallel(paths ? ctx->io_threads : ctx->pack_threads, src, len, doff, w.i0, w.i1, lo, hi,
+                                  ctx->pin[pin_slot]);
                 if (io_errno.load()) {
                     const int e = io_errno.load();
                     CU_TRY(ctx, cudaDeviceSynchronize());
@@ -459,6 +500,27 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
         CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->s_copy));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_copied[slot], 0));
         const uint64_t cnt = w.i1 - w.i0;
+        if (w.seg) {
+            if (w.seg_first) {
+                ChainState iv;
+                memcpy(iv.sha, kShaIv, sizeof kShaIv);
+                memcpy(iv.md5, kMd5Iv, sizeof kMd5Iv);
+                iv.prior_bytes = 0;
+                iv.reserved = 0;
+                CU_TRY(ctx, cudaMemcpyAsync(d_segstate, &iv, sizeof iv, cudaMemcpyHostToDevice, ctx->s_comp));
+            }
+            const uint64_t meta[2] = {0, w.bytes};
+            CU_TRY(ctx, cudaMemcpyAsync(d_segmeta, meta, sizeof meta, cudaMemcpyHostToDevice, ctx->s_comp));
+            const uint32_t f = (flags & 3u) | (w.seg == 2 ? 0u : 0x80000000u);
+            if (int rc = enqueue_device_batch(ctx, ctx->dwave[slot], d_segmeta, d_segmeta + 1, 1, f,
+                                              d_sha ? d_sha + 32 * w.i0 : nullptr, d_md5 ? d_md5 + 16 * w.i0 : nullptr,
+                                              nullptr, d_segstate, ctx->s_comp))
+                return rc;
+            if (w.seg == 2)
+                CU_TRY(ctx, cudaMemcpyAsync(d_trim + w.i0, d_len + w.i0, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->s_comp));
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[slot], ctx->s_comp));
+            continue;
+        }
         if (int rc = enqueue_device_batch(ctx, ctx->dwave[slot], d_off + w.i0, d_len + w.i0, cnt, flags,
                                           d_sha ? d_sha + 32 * w.i0 : nullptr, d_md5 ? d_md5 + 16 * w.i0 : nullptr,
                                           d_trim + w.i0, nullptr, ctx->s_comp))
@@ -732,9 +794,6 @@ int b200h_hash_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, const
 
 // ------------------------------------------------------------------------------------------ streaming
 
-static const uint32_t kShaIv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,
-                                   0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
-static const uint32_t kMd5Iv[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
 
 static int stream_write_iv(b200h_stream* s) {
     b200h_ctx* ctx = s->ctx;

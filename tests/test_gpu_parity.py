@@ -300,3 +300,39 @@ def test_native_file_reader_matches_memory_path_and_reports_io_errors(ctx, tmp_p
         ctx.hash_files(paths, sizes, 0, BOTH)
     s2, _, _ = ctx.hash_files(paths[:3], sizes[:3], 0, _lib.SHA256)  # the context is still usable
     assert s2[2].tobytes() == c_oracle.sha256(blobs[2])
+
+
+def test_messages_larger_than_the_staging_wave_are_segmented():
+    """A context with tiny staging (1 MiB waves) must hash multi-MiB messages by carrying the chaining state
+    across waves -- from pageable memory, from page-locked memory and from files -- mixed with small messages."""
+    c = _lib.Context(0, pinned_bytes=1 << 20, device_bytes=2 << 20)
+    try:
+        lens = np.array([100, 5 * (1 << 20) + 77, 0, 3 * (1 << 20), 64, (1 << 20) - 16, (1 << 20) - 15, 2_500_001], np.uint64)
+        offs = (np.concatenate([[0], np.cumsum(lens + 5)])[:-1] + 3).astype(np.uint64)
+        buf = synth_array(60, int(offs[-1] + lens[-1]) + 16)
+        s, m, _ = c_oracle.hash_batch(buf, offs, lens)
+        for flags in (BOTH, _lib.SHA256, _lib.MD5):
+            sha, md5, trimmed = c.hash_batch_host(buf, offs, lens, flags)
+            assert np.array_equal(trimmed, lens)
+            assert sha is None or np.array_equal(sha, s)
+            assert md5 is None or np.array_equal(md5, m)
+        pinned = c.host_alloc(buf.size)
+        pinned[:] = buf
+        sha, md5, _ = c.hash_batch_host(pinned, offs, lens, BOTH)
+        assert np.array_equal(sha, s) and np.array_equal(md5, m)
+        c.host_free(pinned)
+        with pytest.raises(_lib.B200HashError, match="TRIM_ZEROS"):
+            c.hash_batch_host(buf, offs, lens, BOTH | _lib.TRIM_ZEROS)
+        import tempfile, os
+
+        with tempfile.TemporaryDirectory() as d:
+            paths = []
+            for i, (o, n) in enumerate(zip(offs, lens)):
+                p = os.path.join(d, f"f{i}")
+                buf[int(o) : int(o + n)].tofile(p)
+                paths.append(p)
+            sizes, _ = c.stat_files(paths)
+            sha, md5, _ = c.hash_files(paths, sizes, 0, BOTH)
+            assert np.array_equal(sha, s) and np.array_equal(md5, m)
+    finally:
+        c.close()
