@@ -336,3 +336,12 @@ def test_messages_larger_than_the_staging_wave_are_segmented():
             assert np.array_equal(sha, s) and np.array_equal(md5, m)
     finally:
         c.close()
+
+
+def test_bit_length_beyond_32_bits(ctx):
+    """>= 512 MiB: the message bit length needs the high word (SHA-256 big-endian, MD5 little-endian)."""
+    n = (512 << 20) + 4099
+    data = synth_array(61, n)
+    sha, md5, _ = ctx.hash_batch_host(data, [0], [n], BOTH)
+    assert sha[0].tobytes() == hashlib.sha256(data).digest()
+    assert md5[0].tobytes() == hashlib.md5(data).digest()
