@@ -68,13 +68,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self) -> dict:
-        if not self.proc:
+    def halt(self) -> list:
+        """Stop sampling and return the raw rows (lets a caller merge several timed regions)."""
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+        return self.rows
+
+    @staticmethod
+    def summarize(rows: list, available: bool = True) -> dict:
+        if not available:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
@@ -85,6 +91,10 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self) -> dict:
+        rows = self.halt()
+        return self.summarize(rows, self.proc is not None)
 
 
 def env_rank():
@@ -207,6 +217,7 @@ def run_gpu(args) -> None:
     kern_ms, kern_n = ctx.profile_read()
     ctx.profile_enable(False)
     launches = ctx.launch_count - launches0
+    clock_rows = sampler.halt() if rank == 0 else []
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -229,12 +240,17 @@ def run_gpu(args) -> None:
     for _ in range(max(1, min(args.warmup, 3))):  # warm-up (first call allocates the wave buffers)
         table = e2e_step()
     barrier()
+    sampler2 = ClockSampler(local_rank)
+    if rank == 0:
+        sampler2.start()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         table = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions (HBM-resident and e2e)
+    clocks = None
+    if rank == 0:  # clocks sampled inside the two timed regions only (HBM-resident steps and e2e steps)
+        clocks = ClockSampler.summarize(clock_rows + sampler2.halt(), sampler.proc is not None)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
