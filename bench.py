@@ -110,11 +110,32 @@ def cpu_payloads(n: int, seed: int) -> list[bytes]:
     return [synth_bytes(seed, MSG_BYTES, start=i * MSG_BYTES) for i in range(n)]
 
 
-def run_cpu_pool(payloads: list[bytes], workers: int) -> float:
-    from oracle import ref_port  # allowed here: CPU baseline / reference arm only
+_REF = None
 
+
+def reference_hasher():
+    """(callable, kind): the reference's OWN ``get_upload_hashes`` (unmodified hash_utils.py from baseline/_ref or
+    /root/reference, loaded through oracle/ref_shim.py) -> kind "reference"; if no copy travelled, the hashlib
+    port in oracle/ref_port.py -> kind "port".  Both make exactly the same hashlib calls."""
+    global _REF
+    if _REF is None:
+        from oracle import ref_port, ref_shim  # allowed here: CPU baseline / reference arm only
+
+        try:
+            h, _, _ = ref_shim.load()
+            _REF = (h.get_upload_hashes, "reference")
+        except Exception:
+            _REF = (ref_port.upload_hashes, "port")
+    return _REF
+
+
+def run_cpu_pool(payloads: list[bytes], workers: int) -> float:
+    from concurrent.futures import ThreadPoolExecutor
+
+    fn, _ = reference_hasher()
     t0 = time.perf_counter()
-    ref_port.hash_payloads_pool(payloads, workers)
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        list(ex.map(fn, payloads))
     return time.perf_counter() - t0
 
 
@@ -141,13 +162,15 @@ def run_reference(args) -> None:
     times = [run_cpu_pool(payloads, workers) for _ in range(args.steps)]
     total = sum(times)
     gibs = sample_n * MSG_BYTES * args.steps / GiB / total
-    sample = f"{sample_n} of {N_MSG} payloads x {MSG_BYTES // 1024} KiB per step, hashlib SHA-256+MD5 via get_upload_hashes port, ThreadPool({workers})"
+    what = "the reference's own get_upload_hashes" if reference_hasher()[1] == "reference" else "get_upload_hashes port"
+    sample = f"{sample_n} of {N_MSG} payloads x {MSG_BYTES // 1024} KiB per step, hashlib SHA-256+MD5 via {what}, ThreadPool({workers})"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(gibs, 3), "unit": "GiB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": round(gibs, 3), "unit": "GiB/s", "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(gibs, 3), "unit": "GiB/s", "cores": workers, "kind": reference_hasher()[1],
+                         "sample": sample},
         "e2e": {"value": round(gibs, 3), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -263,25 +286,29 @@ def run_gpu(args) -> None:
     cpu = None
     parity = "host==device tables: %s" % ("exact" if same else "MISMATCH")
     if rank == 0 and world == 1:
-        from oracle import ref_port  # cpu_baseline leg only
-
         sample_n = int(os.environ.get("B200H_CPU_SAMPLE", 16384))
         sample_n = min(sample_n, N_MSG)
         payloads = [host[i * MSG_BYTES:(i + 1) * MSG_BYTES].tobytes() for i in range(sample_n)]
+        from concurrent.futures import ThreadPoolExecutor
+
+        ref_fn, ref_kind = reference_hasher()
         workers = best_pool_workers(payloads[:4096])
         t0 = time.perf_counter()
-        hashes = ref_port.hash_payloads_pool(payloads, workers)
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            hashes = list(ex.map(ref_fn, payloads))
         pool_s = time.perf_counter() - t0
         serial_n = min(2048, sample_n)
         t0 = time.perf_counter()
-        ref_port.hash_payloads_serial(payloads[:serial_n])
+        for p_ in payloads[:serial_n]:
+            ref_fn(p_)
         serial_s = time.perf_counter() - t0
         ok = all(h.sha256_hex() == table.sha256_hex(i) and h.md5_hex() == table.md5_hex(i)
                  for i, h in enumerate(hashes))
         parity += "; GPU vs hashlib on %d payloads: %s" % (sample_n, "exact" if ok else "MISMATCH")
-        cpu = {"value": round(sample_n * MSG_BYTES / GiB / pool_s, 3), "unit": "GiB/s", "cores": workers, "kind": "port",
+        cpu = {"value": round(sample_n * MSG_BYTES / GiB / pool_s, 3), "unit": "GiB/s", "cores": workers, "kind": ref_kind,
                "sample": f"first {sample_n} of {N_MSG} payloads ({sample_n * MSG_BYTES / GiB:.1f} GiB), hashlib SHA-256+MD5 "
-                         f"(get_upload_hashes port), ThreadPool({workers})",
+                         f"({'reference get_upload_hashes' if ref_kind == 'reference' else 'get_upload_hashes port'}), "
+                         f"ThreadPool({workers})",
                "serial_value": round(serial_n * MSG_BYTES / GiB / serial_s, 3),
                "serial_note": "one thread, as the reference's map pump really runs it (blob_utils.py:345)"}
     ctx.host_free(host)

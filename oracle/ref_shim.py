@@ -1,4 +1,4 @@
-"""oracle/ref_shim.py -- TEST INFRASTRUCTURE ONLY; works only where /root/reference exists.
+"""oracle/ref_shim.py -- TEST INFRASTRUCTURE ONLY; needs a copy of the reference (/root/reference or baseline/_ref).
 
 Loads the reference's UNMODIFIED hash_utils.py / blob_utils.py / bytes_io_segment_payload.py
 straight from /root/reference/py/modal/_utils without grpclib / synchronicity / generated
@@ -16,12 +16,30 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("B200H_REFERENCE_ROOT", "/root/reference")
-_PKG = os.path.join(REF_ROOT, "py", "modal")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _candidates():
+    """Where an unmodified copy of the reference's ``modal`` package may live: the mounted reference tree
+    (build container), or ``baseline/_ref`` -- the offline ``pip install --target`` of /root/reference/py that
+    ``__graft_entry__.build()`` makes; it is git-ignored but travels to the GPU box with the snapshot."""
+    env = os.environ.get("B200H_REFERENCE_ROOT")
+    if env:
+        yield os.path.join(env, "py", "modal")
+        yield os.path.join(env, "modal")
+    yield "/root/reference/py/modal"
+    yield os.path.join(_REPO, "baseline", "_ref", "modal")
+
+
+def package_dir() -> str | None:
+    for c in _candidates():
+        if os.path.isfile(os.path.join(c, "_utils", "hash_utils.py")):
+            return c
+    return None
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(_PKG, "_utils", "hash_utils.py"))
+    return package_dir() is not None
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:
@@ -39,8 +57,9 @@ def load():
     global _loaded
     if _loaded is not None:
         return _loaded
-    if not available():
-        raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+    pkg = package_dir()
+    if pkg is None:
+        raise RuntimeError("no copy of the reference found (/root/reference or baseline/_ref)")
     if "modal" in sys.modules and not getattr(sys.modules["modal"], "_b200h_shim", False):
         raise RuntimeError("a real `modal` package is already imported; shim needs a clean process")
 
@@ -65,7 +84,7 @@ def load():
     _stub("modal.config", logger=logging.getLogger("modal-ref"), config={})
     _stub("modal.exception", ExecutionError=ExecutionError)
     utils = _stub("modal._utils")
-    utils.__path__ = [os.path.join(_PKG, "_utils")]
+    utils.__path__ = [os.path.join(pkg, "_utils")]
     _stub(
         "modal._utils.async_utils",
         retry=retry,
