@@ -231,7 +231,7 @@ class Context:
     # -- batch over device memory (raw pointers: torch tensors' data_ptr())
     def hash_batch_device(self, d_base: int, d_offsets: int, d_lengths: int, n: int, flags: int, d_sha: int, d_md5: int,
                           d_trimmed: int = 0, stream: int = 0):
-        rc = self._L.b200h_hash_batch_device(self._h, d_base, d_offsets, d_lengths, n, flags, d_sha or None,
+        rc = self._L.b200h_hash_batch_device(self._h, d_base or None, d_offsets, d_lengths, n, flags, d_sha or None,
                                              d_md5 or None, d_trimmed or None, stream or None)
         self._check(rc, "b200h_hash_batch_device")
 

@@ -70,4 +70,38 @@ def hash_table_buffers(bufs: Sequence, *, sha256: bool = True, md5: bool = True,
     return DigestTable(s, m, t)
 
 
-__all__ = ["DigestTable", "hash_table_host", "hash_table_buffers", "Context", "default_context", "_lib"]
+def hash_table_tensors(tensors: Sequence, *, sha256: bool = True, md5: bool = True, ctx: Context | None = None):
+    """Digest the raw bytes of CUDA tensors where they are (no host round trip): message i is the storage of
+    contiguous tensor i.  Returns ``(sha uint8[n,32] | None, md5 uint8[n,16] | None)`` as CUDA tensors on the
+    same device, ordered on the current torch stream.  This is the entry point for map inputs that are already
+    tensors in HBM: nothing is pickled or copied before hashing."""
+    import torch
+
+    ctx = ctx or default_context()
+    n = len(tensors)
+    dev = tensors[0].device if n else torch.device("cuda", ctx.device)
+    for t in tensors:
+        if not (t.is_cuda and t.is_contiguous() and t.device == dev):
+            raise ValueError("hash_table_tensors needs contiguous CUDA tensors on one device")
+    addr = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64)
+    size = torch.tensor([t.numel() * t.element_size() for t in tensors], dtype=torch.int64)
+    d_addr, d_size = addr.to(dev, non_blocking=False), size.to(dev, non_blocking=False)
+    d_sha = torch.empty((n, 32), dtype=torch.uint8, device=dev) if sha256 else None
+    d_md5 = torch.empty((n, 16), dtype=torch.uint8, device=dev) if md5 else None
+    flags = (SHA256 if sha256 else 0) | (MD5 if md5 else 0)
+    stream = torch.cuda.current_stream(dev)
+    # absolute device addresses as offsets from a NULL base
+    ctx.hash_batch_device(0, d_addr.data_ptr(), d_size.data_ptr(), n, flags, d_sha.data_ptr() if sha256 else 0,
+                          d_md5.data_ptr() if md5 else 0, 0, stream.cuda_stream)
+    # the library launched on this stream (or, for the legacy default stream, on its own): make the result
+    # visible to the caller's stream before the offset tensors can be freed
+    if stream.cuda_stream == 0:
+        torch.cuda.synchronize(dev)
+    else:
+        d_addr.record_stream(stream)
+        d_size.record_stream(stream)
+    return d_sha, d_md5
+
+
+__all__ = ["DigestTable", "hash_table_host", "hash_table_buffers", "hash_table_tensors", "Context", "default_context",
+           "_lib"]

@@ -345,3 +345,23 @@ def test_bit_length_beyond_32_bits(ctx):
     sha, md5, _ = ctx.hash_batch_host(data, [0], [n], BOTH)
     assert sha[0].tobytes() == hashlib.sha256(data).digest()
     assert md5[0].tobytes() == hashlib.md5(data).digest()
+
+
+def test_hash_tensors_in_place(ctx):
+    """Tensors that already live in HBM are hashed where they are (absolute device addresses, NULL base)."""
+    import torch
+
+    from modal_client_b200 import batch
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    tensors = [torch.randn(257, 129, device="cuda", generator=g), torch.arange(100_003, device="cuda", dtype=torch.int32),
+               torch.zeros(0, device="cuda"), torch.randint(0, 255, (3, 70_001), device="cuda", dtype=torch.uint8, generator=g),
+               torch.randn(1 << 20, device="cuda", generator=g).to(torch.bfloat16)]
+    with torch.cuda.stream(torch.cuda.Stream()):
+        sha, md5 = batch.hash_table_tensors(tensors, ctx=ctx)
+        torch.cuda.current_stream().synchronize()
+    for t, s, m in zip(tensors, sha.cpu().numpy(), md5.cpu().numpy()):
+        raw = t.view(torch.uint8).cpu().numpy().tobytes() if t.numel() else b""
+        assert s.tobytes() == c_oracle.sha256(raw) and m.tobytes() == c_oracle.md5(raw)
+    sha2, _ = batch.hash_table_tensors(tensors[:2], md5=False, ctx=ctx)  # legacy default stream path
+    assert sha2[1].cpu().numpy().tobytes() == c_oracle.sha256(tensors[1].cpu().numpy().tobytes())
