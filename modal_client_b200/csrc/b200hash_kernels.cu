@@ -102,7 +102,15 @@ __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0,
 #else
 #define ADD(x, y) addf((x), (y), one)
 #endif
-#if B200H_ADDMODE == 2
+#if B200H_ADDMODE == 3
+// mode 3: only the last sum of a round (new a = T1 + Sigma0 + Maj) is a 3-input IADD3 on the ALU pipe
+#define SHA_RND(a, b, c, d, e, f, g, h, K, W)                                         \
+    {                                                                                 \
+        uint32_t t1 = ADD(ADD(ADD(h, ADD(W, K)), lop3<0xCA>(e, f, g)), SHA_S1(e));    \
+        d = ADD(d, t1);                                                               \
+        h = t1 + SHA_S0(a) + lop3<0xE8>(a, b, c);                                     \
+    }
+#elif B200H_ADDMODE == 2
 #define SHA_RND(a, b, c, d, e, f, g, h, K, W)                                  \
     {                                                                          \
         uint32_t t1 = ADD(h, ADD(W, K)) + SHA_S1(e) + lop3<0xCA>(e, f, g);     \
