@@ -80,10 +80,27 @@ class VolumeUploadContextManager(_BatchBase):
             specs.append(await asyncio.to_thread(blob_utils.get_file_upload_spec_from_fileobj, fp, remote, mode))
         logger.debug(f"Computed checksums for {len(specs)} files on the GPU")
         sem = asyncio.Semaphore(20)  # upload concurrency of the reference (volume.py:1220)
+        # In-batch dedupe on the digest table (what Mount does with a set, py/modal/mount.py:498,518-534): each
+        # distinct content is checked / uploaded once, however many paths carry it.
+        first_of: dict[str, asyncio.Future] = {}
 
         async def one(spec):
-            async with sem:
-                return await self._upload_file(spec)
+            owner = first_of.get(spec.sha256_hex)
+            if owner is not None:
+                await owner
+                self._progress_cb(task_id=self._progress_cb(name=spec.mount_filename, size=spec.size), complete=True)
+                return _wire.MountFile(filename=spec.mount_filename, sha256_hex=spec.sha256_hex, mode=spec.mode)
+            fut = asyncio.get_running_loop().create_future()
+            first_of[spec.sha256_hex] = fut
+            try:
+                async with sem:
+                    out = await self._upload_file(spec)
+                fut.set_result(None)
+                return out
+            except BaseException as exc:
+                fut.set_exception(exc)
+                fut.exception()  # mark retrieved; waiters re-raise it
+                raise
 
         files = list(await gather_cancel_on_error(*(one(s) for s in specs)))
         self._progress_cb(complete=True)

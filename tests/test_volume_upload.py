@@ -113,6 +113,9 @@ def test_batch_upload_v1_dedupes_and_uploads(backend, monkeypatch, tmp_path):
             assert stub.volume_files["/data/dup.bin"][0] == files["sub/b.bin1"]
             assert stub.volume_files["/data/from_fileobj"][0] == b"hello world, this is a lot of text"
             assert len(store.blobs) == 2  # only the two files >= LARGE_FILE_LIMIT became blobs
+            # dup.bin has the content of sub/b.bin1: one existence check + one data put for both paths
+            n_files = len(files) + 2
+            assert stub.mount_put_calls == 2 * (n_files - 1)
             # uploading again without force collides
             with pytest.raises(FileExistsError):
                 async with volume.VolumeUploadContextManager("vo-1", client) as batch:
