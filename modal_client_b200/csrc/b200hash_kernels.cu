@@ -1082,16 +1082,6 @@ __global__ void fill_synth_kernel(uint8_t* __restrict__ dst, uint64_t nbytes, ui
     }
 }
 
-// off[i] = i*part_len, len[i] = min(part_len, total - off[i])  (multipart parts / 8 MiB blocks of one buffer)
-__global__ void iota_parts_kernel(uint64_t* off, uint64_t* len, uint64_t total, uint64_t part_len, uint64_t nparts) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nparts;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t o = i * part_len;
-        off[i] = o;
-        len[i] = total - o < part_len ? total - o : part_len;
-    }
-}
-
 // --------------------------------------------------------------------------------- launch wrappers
 
 static int grid_for(uint64_t n, int threads, int cap) {
@@ -1203,13 +1193,6 @@ int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t sta
     if (!nbytes) return 0;
     fill_synth_kernel<<<grid_for((nbytes >> 3) + 1, 256, 148 * 16), 256, 0, st>>>(dst, nbytes, seed * 0xD1342543DE82EF95ull,
                                                                                  start >> 3);
-    return 1;
-}
-
-int launch_iota_parts(uint64_t* off, uint64_t* len, uint64_t total, uint64_t part_len, uint64_t nparts,
-                      cudaStream_t st) {
-    if (!nparts) return 0;
-    iota_parts_kernel<<<grid_for(nparts, 256, 148 * 4), 256, 0, st>>>(off, len, total, part_len, nparts);
     return 1;
 }
 

@@ -42,8 +42,6 @@ int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* l
                      uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out,
                      ChainState* state /*n entries: caller states (F_NO_FINAL / resume) or scratch*/, cudaStream_t st);
 int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t start, cudaStream_t st);
-int launch_iota_parts(uint64_t* off, uint64_t* len, uint64_t total, uint64_t part_len, uint64_t nparts,
-                      cudaStream_t st);
 
 cudaError_t configure_kernels();  // one-time cudaFuncSetAttribute calls for the current device
 const char* kernel_build_info();
