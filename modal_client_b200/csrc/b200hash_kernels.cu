@@ -99,26 +99,88 @@ __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0,
 #endif
 #if B200H_ADDMODE == 0
 #define ADD(x, y) ((x) + (y))
+#elif B200H_ADDMODE == 4
+// mode 4: single two-input PTX adds (ptxas: VIADD / IADD3 as it sees fit, no forced multiply)
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm volatile("add.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+#define ADD(x, y) add2((x), (y))
+#elif B200H_ADDMODE == 5
+// mode 5: scalar video add (experiment: does ptxas keep it as a two-input VIADD?)
+__device__ __forceinline__ uint32_t addv(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("vadd.u32.u32.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+#define ADD(x, y) addv((x), (y))
 #else
 #define ADD(x, y) addf((x), (y), one)
 #endif
+// B200H_SHAONLY_ROT: in the SHA-256-only instantiation the ALU pipe carries 1040 of the 1640 instructions
+// per block while the FMA pipe idles, so some shifts are moved over as multiplies:
+//   bit 0 / bit 1: the outer rotate of Sigma1 / Sigma0 (Sigma1(e) = rotr6(e ^ rotr5(e) ^ rotr19(e)),
+//                  Sigma0(a) = rotr2(a ^ rotr11(a) ^ rotr20(a))) is a widening multiply x * 2^(32-n) ->
+//                  {x << (32-n), x >> n}; the halves have disjoint bits, so both are simply added into the
+//                  round sum (one SHF less, one IMAD.WIDE + one IMAD more);
+//   bit 2:         the plain shifts of sigma0/sigma1 are IMAD.HI by 2^(32-n) (multiplier in a register so that
+//                  ptxas cannot turn it back into a shift).
+// Measured on B200 (100000 x 256 KiB, SHA-256 only): see profiles/r1_sha_only_rot.md.  The fused kernel does not
+// use it (its FMA pipe is already loaded with MD5's adds: -9 % there), IMAD.WIDE issues at 0.18/clk/SMSP.
+#ifndef B200H_SHAONLY_ROT
+#define B200H_SHAONLY_ROT 3
+#endif
+__device__ __forceinline__ void rotw(uint32_t x, uint32_t mul, uint32_t& lo, uint32_t& hi) {
+    uint64_t d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(x), "r"(mul));
+    lo = (uint32_t)d;
+    hi = (uint32_t)(d >> 32);
+}
+__device__ __forceinline__ uint32_t mulhi(uint32_t x, uint32_t m) {
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(m));
+    return d;
+}
+template <int ROT>
+__device__ __forceinline__ void sha_rnd_rot(uint32_t a, uint32_t b, uint32_t c, uint32_t& d, uint32_t e, uint32_t f,
+                                            uint32_t g, uint32_t& h, uint32_t K, uint32_t W, uint32_t one) {
+    uint32_t t1 = addf(addf(h, addf(W, K, one), one), lop3<0xCA>(e, f, g), one);
+    if (ROT & 1) {
+        uint32_t lo, hi;
+        rotw(lop3<0x96>(e, rotr(e, 5), rotr(e, 19)), 1u << 26, lo, hi);
+        t1 = addf(addf(t1, lo, one), hi, one);
+    } else {
+        t1 = addf(t1, lop3<0x96>(rotr(e, 6), rotr(e, 11), rotr(e, 25)), one);
+    }
+    uint32_t t2;
+    if (ROT & 2) {
+        uint32_t lo, hi;
+        rotw(lop3<0x96>(a, rotr(a, 11), rotr(a, 20)), 1u << 30, lo, hi);
+        t2 = addf(addf(lo, hi, one), lop3<0xE8>(a, b, c), one);
+    } else {
+        t2 = addf(lop3<0x96>(rotr(a, 2), rotr(a, 13), rotr(a, 22)), lop3<0xE8>(a, b, c), one);
+    }
+    d = addf(d, t1, one);
+    h = addf(t1, t2, one);
+}
 #if B200H_ADDMODE == 3
 // mode 3: only the last sum of a round (new a = T1 + Sigma0 + Maj) is a 3-input IADD3 on the ALU pipe
-#define SHA_RND(a, b, c, d, e, f, g, h, K, W)                                         \
+#define SHA_RND_BASE(a, b, c, d, e, f, g, h, K, W)                                         \
     {                                                                                 \
         uint32_t t1 = ADD(ADD(ADD(h, ADD(W, K)), lop3<0xCA>(e, f, g)), SHA_S1(e));    \
         d = ADD(d, t1);                                                               \
         h = t1 + SHA_S0(a) + lop3<0xE8>(a, b, c);                                     \
     }
 #elif B200H_ADDMODE == 2
-#define SHA_RND(a, b, c, d, e, f, g, h, K, W)                                  \
+#define SHA_RND_BASE(a, b, c, d, e, f, g, h, K, W)                                  \
     {                                                                          \
         uint32_t t1 = ADD(h, ADD(W, K)) + SHA_S1(e) + lop3<0xCA>(e, f, g);     \
         d = ADD(d, t1);                                                        \
         h = t1 + SHA_S0(a) + lop3<0xE8>(a, b, c);                              \
     }
 #else
-#define SHA_RND(a, b, c, d, e, f, g, h, K, W)                                         \
+#define SHA_RND_BASE(a, b, c, d, e, f, g, h, K, W)                                         \
     {                                                                                 \
         uint32_t t1 = ADD(ADD(ADD(h, ADD(W, K)), lop3<0xCA>(e, f, g)), SHA_S1(e));    \
         uint32_t t2 = ADD(SHA_S0(a), lop3<0xE8>(a, b, c));                            \
@@ -126,15 +188,33 @@ __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0,
         h = ADD(t1, t2);                                                              \
     }
 #endif
+// kShaRot (a constant inside compress<>) is B200H_SHAONLY_ROT for the SHA-only instantiation, else 0
+#define SHA_RND(a, b, c, d, e, f, g, h, K, W)                                           \
+    {                                                                                   \
+        if (kShaRot & 3) sha_rnd_rot<kShaRot>(a, b, c, d, e, f, g, h, K, W, one);       \
+        else SHA_RND_BASE(a, b, c, d, e, f, g, h, K, W)                                 \
+    }
+#define SHA_SHR3(x) ((kShaRot & 4) ? mulhi((x), m29) : ((x) >> 3))
+#define SHA_SHR10(x) ((kShaRot & 4) ? mulhi((x), m22) : ((x) >> 10))
+#define SHA_s0r(x) lop3<0x96>(rotr(x, 7), rotr(x, 18), SHA_SHR3(x))
+#define SHA_s1r(x) lop3<0x96>(rotr(x, 17), rotr(x, 19), SHA_SHR10(x))
 // message schedule in place: w[i&15] becomes W[i] for i >= 16
 #define SHA_SCHED(w, i) \
-    (w[(i)&15] = ADD(ADD(ADD(w[(i)&15], w[((i)-7) & 15]), SHA_s0(w[((i)-15) & 15])), SHA_s1(w[((i)-2) & 15])))
+    (w[(i)&15] = ADD(ADD(ADD(w[(i)&15], w[((i)-7) & 15]), SHA_s0r(w[((i)-15) & 15])), SHA_s1r(w[((i)-2) & 15])))
 
 // Fused kernel: every add of an MD5 step on the FMA pipe (the ALU pipe is saturated by SHA-256's shifts).
+#if defined(B200H_MD5LEA) && B200H_MD5LEA
+// b + rotl(t, s) left to ptxas: it fuses the rotate and the add into one ALU-pipe LEA.HI (one FMA add less per step)
+#define MD5_STEP_FMA(FN, a, b, c, d, xk, s, T)             \
+    {                                                      \
+        a = b + rotl(ADD(ADD(a, ADD(xk, T)), FN(b, c, d)), s); \
+    }
+#else
 #define MD5_STEP_FMA(FN, a, b, c, d, xk, s, T)             \
     {                                                      \
         a = ADD(b, rotl(ADD(ADD(a, ADD(xk, T)), FN(b, c, d)), s)); \
     }
+#endif
 // MD5-only kernel: there the FMA pipe is the bottleneck (4 IMAD vs 2 ALU ops per step), so the 3-input sum
 // goes back to the ALU pipe as one IADD3: per step ALU = LOP3 + IADD3 + SHF, FMA = (x+T) and (+b).
 #define MD5_STEP_MIX(FN, a, b, c, d, xk, s, T)             \
@@ -151,6 +231,9 @@ __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0,
 
 #ifndef B200H_ROLLED
 #define B200H_ROLLED 0
+#endif
+#ifndef B200H_ILV
+#define B200H_ILV 4
 #endif
 #ifndef B200H_PAIR_GATHER
 #define B200H_PAIR_GATHER 1
@@ -174,6 +257,9 @@ __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], c
                                          bool is_last, uint32_t bits_lo, uint32_t bits_hi, uint32_t one) {
     uint32_t w[16];
     uint32_t m14 = x[14], m15 = x[15];
+    constexpr int kShaRot = DO_MD5 ? 0 : (B200H_SHAONLY_ROT);
+    const uint32_t m29 = one << 29, m22 = one << 22;  // 2^29, 2^22 as run-time values (bit 2 of kShaRot)
+    (void)m29; (void)m22;
     if (DO_SHA) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[i] = bswap(x[i]);
@@ -217,14 +303,43 @@ __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], c
         MD5_STEP(FN, B, C, D, A, x3, s3, t3);                   \
     }
 
-    SHA4(0, 0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u)
-    MD4(MD5_F, x[0], x[1], x[2], x[3], 7, 12, 17, 22, 0xd76aa478u, 0xe8c7b756u, 0x242070dbu, 0xc1bdceeeu)
-    SHA4(4, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u)
-    MD4(MD5_F, x[4], x[5], x[6], x[7], 7, 12, 17, 22, 0xf57c0fafu, 0x4787c62au, 0xa8304613u, 0xfd469501u)
-    SHA4(8, 0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u)
-    MD4(MD5_F, x[8], x[9], x[10], x[11], 7, 12, 17, 22, 0x698098d8u, 0x8b44f7afu, 0xffff5bb1u, 0x895cd7beu)
-    SHA4(12, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u)
-    MD4(MD5_F, x[12], x[13], m14, m15, 7, 12, 17, 22, 0x6b901122u, 0xfd987193u, 0xa679438eu, 0x49b40821u)
+    // B200H_ILV: interleave granularity of the two chains in source order (4 = 4 SHA rounds : 4 MD5 steps).
+#define SHA1(i, K)                                                                   \
+    if (DO_SHA) {                                                                    \
+        if ((i) >= 16) SHA_SCHED(w, (i));                                            \
+        if (((i)&7) == 0) SHA_RND(a, b, c, d, e, f, g, h, K, w[(i)&15])              \
+        else if (((i)&7) == 1) SHA_RND(h, a, b, c, d, e, f, g, K, w[(i)&15])         \
+        else if (((i)&7) == 2) SHA_RND(g, h, a, b, c, d, e, f, K, w[(i)&15])         \
+        else if (((i)&7) == 3) SHA_RND(f, g, h, a, b, c, d, e, K, w[(i)&15])         \
+        else if (((i)&7) == 4) SHA_RND(e, f, g, h, a, b, c, d, K, w[(i)&15])         \
+        else if (((i)&7) == 5) SHA_RND(d, e, f, g, h, a, b, c, K, w[(i)&15])         \
+        else if (((i)&7) == 6) SHA_RND(c, d, e, f, g, h, a, b, K, w[(i)&15])         \
+        else SHA_RND(b, c, d, e, f, g, h, a, K, w[(i)&15])                           \
+    }
+#define MD1(j, FN, xk, s, T)                                  \
+    if (DO_MD5) {                                             \
+        if ((j) == 0) MD5_STEP(FN, A, B, C, D, xk, s, T)      \
+        else if ((j) == 1) MD5_STEP(FN, D, A, B, C, xk, s, T) \
+        else if ((j) == 2) MD5_STEP(FN, C, D, A, B, xk, s, T) \
+        else MD5_STEP(FN, B, C, D, A, xk, s, T)               \
+    }
+#if B200H_ILV == 4
+#define QUAD(i, k0, k1, k2, k3, FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3) \
+    SHA4(i, k0, k1, k2, k3) MD4(FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3)
+#elif B200H_ILV == 2
+#define QUAD(i, k0, k1, k2, k3, FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3) \
+    SHA1(i, k0) SHA1((i) + 1, k1) MD1(0, FN, x0, s0, t0) MD1(1, FN, x1, s1, t1)     \
+    SHA1((i) + 2, k2) SHA1((i) + 3, k3) MD1(2, FN, x2, s2, t2) MD1(3, FN, x3, s3, t3)
+#else
+#define QUAD(i, k0, k1, k2, k3, FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3) \
+    SHA1(i, k0) MD1(0, FN, x0, s0, t0) SHA1((i) + 1, k1) MD1(1, FN, x1, s1, t1)     \
+    SHA1((i) + 2, k2) MD1(2, FN, x2, s2, t2) SHA1((i) + 3, k3) MD1(3, FN, x3, s3, t3)
+#endif
+
+    QUAD(0, 0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, MD5_F, x[0], x[1], x[2], x[3], 7, 12, 17, 22, 0xd76aa478u, 0xe8c7b756u, 0x242070dbu, 0xc1bdceeeu)
+    QUAD(4, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u, MD5_F, x[4], x[5], x[6], x[7], 7, 12, 17, 22, 0xf57c0fafu, 0x4787c62au, 0xa8304613u, 0xfd469501u)
+    QUAD(8, 0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, MD5_F, x[8], x[9], x[10], x[11], 7, 12, 17, 22, 0x698098d8u, 0x8b44f7afu, 0xffff5bb1u, 0x895cd7beu)
+    QUAD(12, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u, MD5_F, x[12], x[13], m14, m15, 7, 12, 17, 22, 0x6b901122u, 0xfd987193u, 0xa679438eu, 0x49b40821u)
 #if B200H_ROLLED
     // Rounds 16..63 as three trips through one copy of the 16-round body (round constants from constant
     // memory), MD5 rounds 2..4 selected per trip: halves the instruction footprint of the hot loop, which
@@ -254,33 +369,24 @@ __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], c
         }
     }
 #else
-    SHA4(16, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu)
-    MD4(MD5_G, x[1], x[6], x[11], x[0], 5, 9, 14, 20, 0xf61e2562u, 0xc040b340u, 0x265e5a51u, 0xe9b6c7aau)
-    SHA4(20, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau)
-    MD4(MD5_G, x[5], x[10], m15, x[4], 5, 9, 14, 20, 0xd62f105du, 0x02441453u, 0xd8a1e681u, 0xe7d3fbc8u)
-    SHA4(24, 0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u)
-    MD4(MD5_G, x[9], m14, x[3], x[8], 5, 9, 14, 20, 0x21e1cde6u, 0xc33707d6u, 0xf4d50d87u, 0x455a14edu)
-    SHA4(28, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u)
-    MD4(MD5_G, x[13], x[2], x[7], x[12], 5, 9, 14, 20, 0xa9e3e905u, 0xfcefa3f8u, 0x676f02d9u, 0x8d2a4c8au)
-    SHA4(32, 0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u)
-    MD4(MD5_H, x[5], x[8], x[11], m14, 4, 11, 16, 23, 0xfffa3942u, 0x8771f681u, 0x6d9d6122u, 0xfde5380cu)
-    SHA4(36, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u)
-    MD4(MD5_H, x[1], x[4], x[7], x[10], 4, 11, 16, 23, 0xa4beea44u, 0x4bdecfa9u, 0xf6bb4b60u, 0xbebfbc70u)
-    SHA4(40, 0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u)
-    MD4(MD5_H, x[13], x[0], x[3], x[6], 4, 11, 16, 23, 0x289b7ec6u, 0xeaa127fau, 0xd4ef3085u, 0x04881d05u)
-    SHA4(44, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u)
-    MD4(MD5_H, x[9], x[12], m15, x[2], 4, 11, 16, 23, 0xd9d4d039u, 0xe6db99e5u, 0x1fa27cf8u, 0xc4ac5665u)
-    SHA4(48, 0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u)
-    MD4(MD5_I, x[0], x[7], m14, x[5], 6, 10, 15, 21, 0xf4292244u, 0x432aff97u, 0xab9423a7u, 0xfc93a039u)
-    SHA4(52, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u)
-    MD4(MD5_I, x[12], x[3], x[10], x[1], 6, 10, 15, 21, 0x655b59c3u, 0x8f0ccc92u, 0xffeff47du, 0x85845dd1u)
-    SHA4(56, 0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u)
-    MD4(MD5_I, x[8], m15, x[6], x[13], 6, 10, 15, 21, 0x6fa87e4fu, 0xfe2ce6e0u, 0xa3014314u, 0x4e0811a1u)
-    SHA4(60, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u)
-    MD4(MD5_I, x[4], x[11], x[2], x[9], 6, 10, 15, 21, 0xf7537e82u, 0xbd3af235u, 0x2ad7d2bbu, 0xeb86d391u)
+    QUAD(16, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, MD5_G, x[1], x[6], x[11], x[0], 5, 9, 14, 20, 0xf61e2562u, 0xc040b340u, 0x265e5a51u, 0xe9b6c7aau)
+    QUAD(20, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau, MD5_G, x[5], x[10], m15, x[4], 5, 9, 14, 20, 0xd62f105du, 0x02441453u, 0xd8a1e681u, 0xe7d3fbc8u)
+    QUAD(24, 0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, MD5_G, x[9], m14, x[3], x[8], 5, 9, 14, 20, 0x21e1cde6u, 0xc33707d6u, 0xf4d50d87u, 0x455a14edu)
+    QUAD(28, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u, MD5_G, x[13], x[2], x[7], x[12], 5, 9, 14, 20, 0xa9e3e905u, 0xfcefa3f8u, 0x676f02d9u, 0x8d2a4c8au)
+    QUAD(32, 0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, MD5_H, x[5], x[8], x[11], m14, 4, 11, 16, 23, 0xfffa3942u, 0x8771f681u, 0x6d9d6122u, 0xfde5380cu)
+    QUAD(36, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u, MD5_H, x[1], x[4], x[7], x[10], 4, 11, 16, 23, 0xa4beea44u, 0x4bdecfa9u, 0xf6bb4b60u, 0xbebfbc70u)
+    QUAD(40, 0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, MD5_H, x[13], x[0], x[3], x[6], 4, 11, 16, 23, 0x289b7ec6u, 0xeaa127fau, 0xd4ef3085u, 0x04881d05u)
+    QUAD(44, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u, MD5_H, x[9], x[12], m15, x[2], 4, 11, 16, 23, 0xd9d4d039u, 0xe6db99e5u, 0x1fa27cf8u, 0xc4ac5665u)
+    QUAD(48, 0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, MD5_I, x[0], x[7], m14, x[5], 6, 10, 15, 21, 0xf4292244u, 0x432aff97u, 0xab9423a7u, 0xfc93a039u)
+    QUAD(52, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u, MD5_I, x[12], x[3], x[10], x[1], 6, 10, 15, 21, 0x655b59c3u, 0x8f0ccc92u, 0xffeff47du, 0x85845dd1u)
+    QUAD(56, 0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, MD5_I, x[8], m15, x[6], x[13], 6, 10, 15, 21, 0x6fa87e4fu, 0xfe2ce6e0u, 0xa3014314u, 0x4e0811a1u)
+    QUAD(60, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u, MD5_I, x[4], x[11], x[2], x[9], 6, 10, 15, 21, 0xf7537e82u, 0xbd3af235u, 0x2ad7d2bbu, 0xeb86d391u)
 #endif
 #undef SHA4
 #undef MD4
+#undef SHA1
+#undef MD1
+#undef QUAD
 
     if (DO_SHA) {
         hs[0] += a; hs[1] += b; hs[2] += c; hs[3] += d;
