@@ -118,6 +118,21 @@ int b200h_stream_digest(b200h_stream* s, uint8_t sha256_out[32], uint8_t md5_out
 int b200h_stream_reset(b200h_stream* s);
 void b200h_stream_free(b200h_stream* s);
 
+/* ---- dedupe of the digest table (the step right after the path) ---------------------------------- */
+
+/* For n fixed-width keys (key_bytes = 32: SHA-256 rows, 16: MD5 rows) compute first[i] = the smallest j with
+ * key_j == key_i (so first[i] == i marks the first occurrence of a content) and the number of distinct keys.
+ * Exact (full-key comparison), deterministic, computed on the device over a hash table in HBM.
+ * Replaces: the `accounted_hashes` set of _Mount._load_mount (py/modal/mount.py:498,518-534), which dedupes one
+ * file at a time on the event loop, and the per-file MountPutFile existence round trips the volumefs1 uploader
+ * spends on duplicates inside one batch (py/modal/volume.py:1288-1296).
+ * _host: keys / first_out are host arrays, blocks until done.  _device: every pointer is a device pointer
+ * (d_keys 4-byte aligned, d_ndistinct may be NULL), work is only enqueued on cuda_stream (NULL = ctx's stream). */
+int b200h_dedupe_host(b200h_ctx* ctx, const uint8_t* keys, uint64_t n, uint32_t key_bytes, uint32_t* first_out,
+                      uint64_t* ndistinct_out);
+int b200h_dedupe_device(b200h_ctx* ctx, const void* d_keys, uint64_t n, uint32_t key_bytes, uint32_t* d_first,
+                        uint64_t* d_ndistinct, void* cuda_stream);
+
 /* ---- utilities ---------------------------------------------------------------------------------- */
 
 /* Counter-based synthetic bytes on the device (bench / test data): d_dst[0..nbytes) = bytes

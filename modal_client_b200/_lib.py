@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "b200h_host_alloc", "b200h_host_free", "b200h_hash_batch_host", "b200h_hash_batch_device",
     "b200h_hash_fixed_parts", "b200h_stat_files", "b200h_hash_files", "b200h_stream_new", "b200h_stream_update", "b200h_stream_digest",
     "b200h_stream_reset", "b200h_stream_free", "b200h_fill_synth_device", "b200h_launch_count",
-    "b200h_profile_enable", "b200h_profile_read",
+    "b200h_profile_enable", "b200h_profile_read", "b200h_dedupe_host", "b200h_dedupe_device",
 )
 
 
@@ -37,7 +37,7 @@ class B200HashError(RuntimeError):
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("b200hash_kernels.cu", "b200hash_api.cu", "b200hash_kernels.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("b200hash_kernels.cu", "b200hash_dedupe.cu", "b200hash_api.cu", "b200hash_kernels.cuh")]
     srcs.append(os.path.join(os.path.dirname(_PKG), "include", "b200hash.h"))
     stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
@@ -109,6 +109,10 @@ def load_library() -> ctypes.CDLL:
         L.b200h_profile_enable.restype = i32
         L.b200h_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
         L.b200h_profile_read.restype = i32
+        L.b200h_dedupe_host.argtypes = [vp, vp, u64, u32, vp, ctypes.POINTER(u64)]
+        L.b200h_dedupe_host.restype = i32
+        L.b200h_dedupe_device.argtypes = [vp, vp, u64, u32, vp, vp, vp]
+        L.b200h_dedupe_device.restype = i32
         _lib = L
         return L
 
@@ -283,6 +287,26 @@ class Context:
                                       _np_ptr(trimmed))
         self._check(rc, "b200h_hash_files")
         return sha, md5, trimmed
+
+    # -- dedupe of a digest table (first occurrence of every content)
+    def dedupe(self, keys: np.ndarray) -> tuple[np.ndarray, int]:
+        """keys: uint8[n, 32] (SHA-256 rows) or uint8[n, 16] (MD5 rows) on the host.
+        -> (first uint32[n] with first[i] = smallest j such that keys[j] == keys[i], number of distinct rows)"""
+        k = np.ascontiguousarray(keys, dtype=np.uint8)
+        if k.ndim != 2 or k.shape[1] not in (16, 32):
+            raise ValueError("keys must be uint8[n, 32] or uint8[n, 16]")
+        n = int(k.shape[0])
+        first = np.empty(n, np.uint32)
+        nd = ctypes.c_uint64()
+        rc = self._L.b200h_dedupe_host(self._h, _np_ptr(k) if n else None, n, k.shape[1], _np_ptr(first) if n else None,
+                                       ctypes.byref(nd))
+        self._check(rc, "b200h_dedupe_host")
+        return first, int(nd.value)
+
+    def dedupe_device(self, d_keys: int, n: int, key_bytes: int, d_first: int, d_ndistinct: int = 0, stream: int = 0):
+        rc = self._L.b200h_dedupe_device(self._h, d_keys or None, n, key_bytes, d_first or None, d_ndistinct or None,
+                                         stream or None)
+        self._check(rc, "b200h_dedupe_device")
 
     def fill_synth_device(self, d_ptr: int, nbytes: int, seed: int, start: int = 0, stream: int = 0):
         self._check(self._L.b200h_fill_synth_device(self._h, d_ptr, nbytes, seed, start, stream or None),

@@ -52,6 +52,27 @@ except Exception:
         function_call_id: str = ""
 
 
+# enum ObjectCreationType, modal_proto/api.proto:207-214
+OBJECT_CREATION_TYPE_UNSPECIFIED = 0
+OBJECT_CREATION_TYPE_CREATE_IF_MISSING = 1
+OBJECT_CREATION_TYPE_CREATE_FAIL_IF_EXISTS = 2
+OBJECT_CREATION_TYPE_ANONYMOUS_OWNED_BY_APP = 4
+OBJECT_CREATION_TYPE_EPHEMERAL = 5
+
+try:  # pragma: no cover
+    from modal_proto.api_pb2 import MountGetOrCreateRequest  # type: ignore
+except Exception:
+
+    @dataclasses.dataclass
+    class MountGetOrCreateRequest:  # type: ignore[no-redef]  (api.proto:2589-2596)
+        deployment_name: str = ""
+        namespace: int = 0
+        environment_name: str = ""
+        object_creation_type: int = OBJECT_CREATION_TYPE_UNSPECIFIED
+        files: list = dataclasses.field(default_factory=list)
+        app_id: str = ""
+
+
 try:  # pragma: no cover
     from modal_proto.api_pb2 import (  # type: ignore
         MountFile, MountPutFileRequest, VolumePutFiles2Request, VolumePutFilesRequest)

@@ -41,6 +41,15 @@ class DigestTable:
     def md5_base64(self, i: int) -> str:
         return base64.b64encode(self.md5[i].tobytes()).decode("ascii")
 
+    def first_occurrence(self, ctx: Context | None = None) -> tuple[np.ndarray, int]:
+        """In-batch dedupe on the GPU: ``first[i]`` = smallest row index carrying the same SHA-256 (MD5 when the
+        table has no SHA-256 column) as row i, and the number of distinct contents.  What ``_Mount._load_mount``
+        does one file at a time with its ``accounted_hashes`` set (py/modal/mount.py:498,518-534)."""
+        keys = self.sha256 if self.sha256 is not None else self.md5
+        if keys is None:
+            raise ValueError("the table holds no digests")
+        return (ctx or default_context()).dedupe(keys)
+
     def packed(self) -> np.ndarray:
         """uint8[n,48]: sha256 || md5 per row -- the table the ranks all-gather."""
         n = len(self)

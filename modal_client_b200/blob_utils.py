@@ -36,7 +36,7 @@ from urllib.parse import urlparse
 
 import numpy as np
 
-from . import _lib, hash_utils
+from . import _lib, _wire, hash_utils
 from ._backend import get_context
 from ._logging import logger
 from ._wire import BlobCreateRequest
@@ -412,6 +412,48 @@ async def blob_upload_file(
     return blob_id
 
 
+# ------------------------------------------------------------------------------------------- download
+
+
+@retry(n_attempts=5, base_delay=0.1)
+async def _download_from_url(download_url: str) -> bytes:
+    """GET one blob (reference :377-388; no integrity check there either: blobs are addressed by id)."""
+    async with ClientSessionRegistry.get_session().get(download_url) as s3_resp:
+        if s3_resp.status == 503:  # S3 SlowDown
+            logger.debug("Received SlowDown signal from S3, sleeping for 1 second before retrying.")
+            await asyncio.sleep(1)
+        if s3_resp.status != 200:
+            text = await s3_resp.text()
+            raise ExecutionError(f"Get from url failed with status {s3_resp.status}: {text}")
+        return await s3_resp.read()
+
+
+async def blob_download(blob_id: str, stub) -> bytes:
+    """Read a whole blob into memory (reference :391-404)."""
+    logger.debug(f"Downloading large blob {blob_id}")
+    t0 = time.time()
+    resp = await stub.BlobGet(_wire.BlobGetRequest(blob_id=blob_id))
+    data = await _download_from_url(resp.download_url)
+    size_mib = len(data) / 1024 / 1024
+    dur_s = max(time.time() - t0, 0.001)
+    logger.debug(f"Downloaded large blob {blob_id} of size {size_mib:.2f} MiB ({size_mib / dur_s:.2f} MiB/s, total {dur_s:.2f}s)")
+    return data
+
+
+async def blob_iter(blob_id: str, stub):
+    """Stream a blob chunk by chunk (reference :407-422)."""
+    resp = await stub.BlobGet(_wire.BlobGetRequest(blob_id=blob_id))
+    async with ClientSessionRegistry.get_session().get(resp.download_url) as s3_resp:
+        if s3_resp.status == 503:
+            logger.debug("Received SlowDown signal from S3, sleeping for 1 second before retrying.")
+            await asyncio.sleep(1)
+        if s3_resp.status != 200:
+            text = await s3_resp.text()
+            raise ExecutionError(f"Get from url failed with status {s3_resp.status}: {text}")
+        async for chunk in s3_resp.content.iter_any():
+            yield chunk
+
+
 # ------------------------------------------------------------------------------- FileUploadSpec (v1)
 
 
@@ -553,6 +595,18 @@ def get_file_upload_specs(
             )
         )
     return specs
+
+
+def first_occurrence_of_specs(specs: Sequence[FileUploadSpec]) -> tuple[list[int], int]:
+    """In-batch dedupe of a list of specs by content (SHA-256), computed on the GPU over the digest table:
+    ``first[i]`` is the index of the first spec with the same content as spec i.  The reference's counterpart is
+    the ``accounted_hashes`` set walked file by file in ``_Mount._load_mount`` (py/modal/mount.py:498,518-534)."""
+    n = len(specs)
+    if n == 0:
+        return [], 0
+    keys = np.frombuffer(bytes.fromhex("".join(s.sha256_hex for s in specs)), np.uint8).reshape(n, 32)
+    first, ndistinct = get_context().dedupe(keys)
+    return first.tolist(), ndistinct
 
 
 # ---------------------------------------------------------------------------- FileUploadSpec2 (v2)

@@ -72,12 +72,14 @@ struct b200h_ctx {
     cudaEvent_t ev_pin[2] = {nullptr, nullptr};       // H2D out of a pinned slot finished
     cudaEvent_t ev_scratch = nullptr;                 // last use of the shared scratch buffers
     bool scratch_used = false;
+    cudaEvent_t ev_dedupe = nullptr;                  // last use of the dedupe table
+    bool dedupe_used = false;
     uint8_t* pin[2] = {nullptr, nullptr};
     size_t pin_cap = 0;  // per slot
     uint8_t* dwave[2] = {nullptr, nullptr};
     size_t dwave_cap = 0;  // per slot
     size_t dwave_want = 0;
-    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small, d_states;
+    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small, d_states, d_dedupe, d_keys;
     uint64_t* h_meta = nullptr;  // pinned: offsets then lengths
     size_t h_meta_cap = 0;       // in uint64 elements
     uint64_t launches = 0;
@@ -623,6 +625,7 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
         CU_INIT(cudaEventCreateWithFlags(&ctx->ev_pin[s], cudaEventDisableTiming));
     }
     CU_INIT(cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming));
+    CU_INIT(cudaEventCreateWithFlags(&ctx->ev_dedupe, cudaEventDisableTiming));
     if (pinned_bytes == 0) pinned_bytes = size_t(512) << 20;
     if (device_bytes == 0) device_bytes = size_t(8) << 30;
     ctx->pin_cap = std::max<size_t>((pinned_bytes / 2) & ~size_t(4095), 1 << 20);
@@ -647,7 +650,7 @@ void b200h_destroy(b200h_ctx* ctx) {
         cudaEventDestroy(pr.second);
     }
     for (DevBuf* b : {&ctx->d_off, &ctx->d_len, &ctx->d_order, &ctx->d_trim, &ctx->d_sha, &ctx->d_md5, &ctx->d_scratch,
-                      &ctx->d_small, &ctx->d_states})
+                      &ctx->d_small, &ctx->d_states, &ctx->d_dedupe, &ctx->d_keys})
         if (b->p) cudaFree(b->p);
     for (int s = 0; s < 2; ++s) {
         if (ctx->dwave[s]) cudaFree(ctx->dwave[s]);
@@ -657,6 +660,7 @@ void b200h_destroy(b200h_ctx* ctx) {
         if (ctx->ev_pin[s]) cudaEventDestroy(ctx->ev_pin[s]);
     }
     if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
+    if (ctx->ev_dedupe) cudaEventDestroy(ctx->ev_dedupe);
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
@@ -916,6 +920,63 @@ void b200h_stream_free(b200h_stream* s) {
     }
     free(s->hbuf);
     delete s;
+}
+
+// ---- dedupe of the digest table ------------------------------------------------------------------
+
+static int dedupe_args_ok(b200h_ctx* ctx, uint64_t n, uint32_t key_bytes) {
+    if (!ctx) return B200H_E_INVALID;
+    if (key_bytes != 32 && key_bytes != 16) return fail(ctx, B200H_E_INVALID, "key_bytes must be 32 (SHA-256) or 16 (MD5)");
+    if (n >= 0x7fffffffull) return fail(ctx, B200H_E_INVALID, "table larger than 2^31-2 rows");
+    return 0;
+}
+
+int b200h_dedupe_device(b200h_ctx* ctx, const void* d_keys, uint64_t n, uint32_t key_bytes, uint32_t* d_first,
+                        uint64_t* d_ndistinct, void* cuda_stream) {
+    if (int rc = dedupe_args_ok(ctx, n, key_bytes)) return rc;
+    if (n && (!d_keys || !d_first)) return fail(ctx, B200H_E_INVALID, "null device pointer");
+    if ((reinterpret_cast<uintptr_t>(d_keys) & 3) != 0) return fail(ctx, B200H_E_INVALID, "d_keys must be 4-byte aligned");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->s_comp;
+    if (int rc = ensure_dev(ctx, ctx->d_dedupe, (size_t)dedupe_table_capacity(n) * 2 * sizeof(uint32_t))) return rc;
+    if (ctx->dedupe_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_dedupe, 0));  // table shared across streams
+    ctx->launches += launch_dedupe(d_keys, n, key_bytes, (uint32_t*)ctx->d_dedupe.p, d_first,
+                                   reinterpret_cast<unsigned long long*>(d_ndistinct), st);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_dedupe, st));
+    ctx->dedupe_used = true;
+    return 0;
+}
+
+int b200h_dedupe_host(b200h_ctx* ctx, const uint8_t* keys, uint64_t n, uint32_t key_bytes, uint32_t* first_out,
+                      uint64_t* ndistinct_out) {
+    if (int rc = dedupe_args_ok(ctx, n, key_bytes)) return rc;
+    if (n && (!keys || !first_out)) return fail(ctx, B200H_E_INVALID, "null pointer");
+    if (n == 0) {
+        if (ndistinct_out) *ndistinct_out = 0;
+        return 0;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->s_comp;
+    // device layout: keys | first[n] | ndistinct (8-byte aligned)
+    const size_t kb = (size_t)n * key_bytes, fb = ((size_t)n * 4 + 7) & ~size_t(7);
+    if (int rc = ensure_dev(ctx, ctx->d_keys, kb + fb + 8)) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_dedupe, (size_t)dedupe_table_capacity(n) * 2 * sizeof(uint32_t))) return rc;
+    uint8_t* d = (uint8_t*)ctx->d_keys.p;
+    uint32_t* d_first = (uint32_t*)(d + kb);
+    unsigned long long* d_cnt = (unsigned long long*)(d + kb + fb);
+    if (ctx->dedupe_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_dedupe, 0));
+    CU_TRY(ctx, cudaMemcpyAsync(d, keys, kb, cudaMemcpyHostToDevice, st));
+    ctx->launches += launch_dedupe(d, n, key_bytes, (uint32_t*)ctx->d_dedupe.p, d_first, d_cnt, st);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaMemcpyAsync(first_out, d_first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    unsigned long long cnt = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    if (ndistinct_out) *ndistinct_out = cnt;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------ utilities

@@ -41,6 +41,10 @@ int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* 
 int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring, int* qctl,
                      uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out,
                      ChainState* state /*n entries: caller states (F_NO_FINAL / resume) or scratch*/, cudaStream_t st);
+// first-occurrence dedupe of a digest table (b200hash_dedupe.cu)
+uint32_t dedupe_table_capacity(uint64_t n);  // slots; the table buffer holds 2x that many uint32 words
+int launch_dedupe(const void* d_keys, uint64_t n, uint32_t key_bytes, uint32_t* table, uint32_t* d_first,
+                  unsigned long long* d_ndistinct, cudaStream_t st);
 int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t start, cudaStream_t st);
 
 cudaError_t configure_kernels();  // one-time cudaFuncSetAttribute calls for the current device

@@ -80,18 +80,19 @@ class VolumeUploadContextManager(_BatchBase):
             specs.append(await asyncio.to_thread(blob_utils.get_file_upload_spec_from_fileobj, fp, remote, mode))
         logger.debug(f"Computed checksums for {len(specs)} files on the GPU")
         sem = asyncio.Semaphore(20)  # upload concurrency of the reference (volume.py:1220)
-        # In-batch dedupe on the digest table (what Mount does with a set, py/modal/mount.py:498,518-534): each
-        # distinct content is checked / uploaded once, however many paths carry it.
-        first_of: dict[str, asyncio.Future] = {}
+        # In-batch dedupe on the digest table, computed on the GPU (b200h_dedupe_host; what Mount does with a set,
+        # py/modal/mount.py:498,518-534): each distinct content is checked / uploaded once, however many paths
+        # carry it; the other paths wait for that upload and only appear in the file index.
+        first, _ = await asyncio.to_thread(blob_utils.first_occurrence_of_specs, specs)
+        loop = asyncio.get_running_loop()
+        done_of = {i: loop.create_future() for i in set(first)}
 
-        async def one(spec):
-            owner = first_of.get(spec.sha256_hex)
-            if owner is not None:
-                await owner
+        async def one(i, spec):
+            if first[i] != i:
+                await done_of[first[i]]
                 self._progress_cb(task_id=self._progress_cb(name=spec.mount_filename, size=spec.size), complete=True)
                 return _wire.MountFile(filename=spec.mount_filename, sha256_hex=spec.sha256_hex, mode=spec.mode)
-            fut = asyncio.get_running_loop().create_future()
-            first_of[spec.sha256_hex] = fut
+            fut = done_of[i]
             try:
                 async with sem:
                     out = await self._upload_file(spec)
@@ -102,7 +103,7 @@ class VolumeUploadContextManager(_BatchBase):
                 fut.exception()  # mark retrieved; waiters re-raise it
                 raise
 
-        files = list(await gather_cancel_on_error(*(one(s) for s in specs)))
+        files = list(await gather_cancel_on_error(*(one(i, s) for i, s in enumerate(specs))))
         self._progress_cb(complete=True)
         request = _wire.VolumePutFilesRequest(volume_id=self._volume_id, files=files,
                                               disallow_overwrite_existing_files=not self._force)

@@ -131,6 +131,22 @@ def multipart_etag(buf, part_len: int) -> tuple[list[bytes], str]:
 # ------------------------------------------------------------------ CPU baseline drivers
 
 
+def first_occurrence(keys) -> tuple[list[int], int]:
+    """In-batch dedupe as py/modal/mount.py:498,518-534 does it: walk the files in order, a content whose digest
+    is already in `accounted_hashes` is skipped, otherwise it is added.  Returned per row: the index of the row
+    that first carried the same digest (== own index for a first occurrence), and the number of distinct digests."""
+    accounted: dict[bytes, int] = {}
+    first = []
+    for i, k in enumerate(keys):
+        k = bytes(k)
+        if k in accounted:  # mount.py:518
+            first.append(accounted[k])
+        else:
+            accounted[k] = i  # mount.py:534
+            first.append(i)
+    return first, len(accounted)
+
+
 def default_workers() -> int:
     """``ThreadPoolExecutor()`` default the reference relies on (volume.py:1211, mount.py:469)."""
     return min(32, (os.cpu_count() or 1) + 4)

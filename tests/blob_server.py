@@ -44,11 +44,19 @@ class BlobStore:
         return web.Response(text=f'<etag>"{cat}-{len(ordered)}"</etag>')
 
 
+    async def download(self, request: web.Request):  # py/test/conftest.py:3393-3397
+        blob_id = request.query["blob_id"]
+        if blob_id == "bl-failure":
+            return web.Response(status=500)
+        return web.Response(body=self.blobs[blob_id])
+
+
 @contextlib.asynccontextmanager
 async def running_blob_server():
     store = BlobStore()
     app = web.Application(client_max_size=1 << 30)
-    app.add_routes([web.put("/upload", store.upload), web.post("/complete_multipart", store.complete)])
+    app.add_routes([web.put("/upload", store.upload), web.post("/complete_multipart", store.complete),
+                    web.get("/download", store.download)])
     runner = web.AppRunner(app)
     await runner.setup()
     site = web.TCPSite(runner, "127.0.0.1", 0)
@@ -67,6 +75,9 @@ class FakeBlobStub:
         self.host, self.threshold, self.providers = host, multipart_threshold, providers
         self.requests = []
         self.n = 0
+
+    async def BlobGet(self, req):  # py/test/conftest.py:1382-1385
+        return types.SimpleNamespace(download_url=f"{self.host}/download?blob_id={req.blob_id}")
 
     async def BlobCreate(self, req):
         self.requests.append(req)

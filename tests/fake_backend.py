@@ -83,6 +83,13 @@ class FakeContext:
     def stream(self, flags=_lib.SHA256 | _lib.MD5):
         return FakeStream(flags)
 
+    def dedupe(self, keys):
+        from oracle import ref_port
+
+        self.calls.append(("dedupe", len(keys)))
+        first, nd = ref_port.first_occurrence(np.asarray(keys, np.uint8))
+        return np.asarray(first, np.uint32), nd
+
     def stat_files(self, paths):
         import os
 

@@ -365,3 +365,60 @@ def test_hash_tensors_in_place(ctx):
         assert s.tobytes() == c_oracle.sha256(raw) and m.tobytes() == c_oracle.md5(raw)
     sha2, _ = batch.hash_table_tensors(tensors[:2], md5=False, ctx=ctx)  # legacy default stream path
     assert sha2[1].cpu().numpy().tobytes() == c_oracle.sha256(tensors[1].cpu().numpy().tobytes())
+
+
+def _np_first(keys):
+    """numpy restatement used at sizes where the dict walk of the oracle is slow: np.unique over rows."""
+    k = np.ascontiguousarray(keys)
+    v = k.view(np.dtype((np.void, k.shape[1]))).ravel()
+    _, idx, inv = np.unique(v, return_index=True, return_inverse=True)
+    return idx[inv].astype(np.uint32), len(idx)
+
+
+@pytest.mark.parametrize("width", [32, 16])
+def test_dedupe_matches_the_mount_set_walk(ctx, width):
+    """b200h_dedupe_host == the `accounted_hashes` walk of mount.py:498,518-534 (oracle.ref_port.first_occurrence)."""
+    rng = np.random.default_rng(width)
+    cases = [
+        np.zeros((0, width), np.uint8),                                           # empty table
+        rng.integers(0, 256, (1, width), dtype=np.uint8),                         # single row
+        np.repeat(rng.integers(0, 256, (1, width), dtype=np.uint8), 1000, 0),     # every row the same content
+        rng.integers(0, 256, (5000, width), dtype=np.uint8),                      # all distinct
+        rng.integers(0, 256, (97, width), dtype=np.uint8)[rng.integers(0, 97, 20000)],  # heavy duplication
+    ]
+    # rows that share the first 8 bytes (same home slot, full-key comparison decides) and differ only in the last byte
+    coll = np.repeat(rng.integers(0, 256, (1, width), dtype=np.uint8), 600, 0)
+    coll[:, -1] = np.arange(600) % 7
+    cases.append(coll)
+    # digests of real (duplicated) contents
+    blobs = [synth_bytes(i % 37, 100 + (i % 37)) for i in range(500)]
+    dig = np.array([np.frombuffer(hashlib.sha256(b).digest() if width == 32 else hashlib.md5(b).digest(), np.uint8)
+                    for b in blobs])
+    cases.append(dig)
+    for keys in cases:
+        first, nd = ctx.dedupe(keys)
+        want, want_nd = ref_port.first_occurrence(keys)
+        assert first.tolist() == want and nd == want_nd
+
+
+def test_dedupe_million_rows_and_device_entry_point(ctx):
+    import torch
+
+    rng = np.random.default_rng(5)
+    pool = rng.integers(0, 256, (300_000, 32), dtype=np.uint8)
+    keys = pool[rng.integers(0, len(pool), 1_000_000)]
+    want, want_nd = _np_first(keys)
+    first, nd = ctx.dedupe(keys)
+    assert np.array_equal(first, want) and nd == want_nd
+    # device-resident table (what the batch path hands over): same answer, nothing leaves HBM but the result
+    d_keys = torch.from_numpy(keys).cuda()
+    d_first = torch.empty(len(keys), dtype=torch.int32, device="cuda")
+    d_nd = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(2):  # the table scratch is reused: a second run must give the same result
+            ctx.dedupe_device(d_keys.data_ptr(), len(keys), 32, d_first.data_ptr(), d_nd.data_ptr(), st.cuda_stream)
+        st.synchronize()
+    assert np.array_equal(d_first.cpu().numpy().view(np.uint32), want) and int(d_nd.item()) == want_nd
+    with pytest.raises(_lib.B200HashError):
+        ctx.dedupe_device(d_keys.data_ptr(), 10, 24, d_first.data_ptr())  # unsupported key width

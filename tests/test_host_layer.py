@@ -219,6 +219,28 @@ def test_blob_upload_single_and_multipart_round_trip(backend, monkeypatch):
     asyncio.run(run())
 
 
+def test_blob_download_round_trip_and_failure(backend, monkeypatch):
+    """blob_download / blob_iter (py/test/blob_test.py:25-46: upload, download, compare; bl-failure -> error)."""
+    monkeypatch.setenv("RETRY_N_ATTEMPTS_OVERRIDE", "2")
+
+    async def run():
+        async with running_blob_server() as (host, store):
+            stub = FakeBlobStub(host, multipart_threshold=1024)
+            for payload in (b"", synth_bytes(92, 700), synth_bytes(93, 5000)):
+                bid = await blob_utils.blob_upload(payload, stub)
+                assert await blob_utils.blob_download(bid, stub) == payload
+                got = b"".join([c async for c in blob_utils.blob_iter(bid, stub)])
+                assert got == payload
+            with pytest.raises(ExecutionError, match="failed with status 500"):
+                await blob_utils.blob_download("bl-failure", stub)
+            with pytest.raises(ExecutionError, match="failed with status 500"):
+                async for _ in blob_utils.blob_iter("bl-failure", stub):
+                    pass
+            await blob_utils.ClientSessionRegistry.close_session()
+
+    asyncio.run(run())
+
+
 def test_upload_integrity_failures(backend, monkeypatch):
     monkeypatch.setenv("RETRY_N_ATTEMPTS_OVERRIDE", "2")
 

@@ -138,3 +138,21 @@ def test_live_reference_agrees_with_port():
         assert b._find_end_of_block(lambda: io.BytesIO(data + bytes(9)), 0, n + 9) == ref_port.block_end(
             data + bytes(9), 0, n + 9
         )
+
+
+def test_first_occurrence_is_the_set_walk_of_the_mount_uploader():
+    """oracle.ref_port.first_occurrence restates mount.py:498,518-534: a digest already accounted for is skipped."""
+    from oracle import ref_port
+
+    keys = [b"a" * 32, b"b" * 32, b"a" * 32, b"c" * 32, b"b" * 32, b"a" * 32]
+    assert ref_port.first_occurrence(keys) == ([0, 1, 0, 3, 1, 0], 3)
+    assert ref_port.first_occurrence([]) == ([], 0)
+    # against the literal reference behaviour: walk with a set, count what would be sent
+    accounted, sent = set(), []
+    for i, k in enumerate(keys):
+        if k in accounted:
+            continue
+        accounted.add(k)
+        sent.append(i)
+    first, nd = ref_port.first_occurrence(keys)
+    assert [i for i, f in enumerate(first) if f == i] == sent and nd == len(accounted)
