@@ -1,0 +1,72 @@
+"""The C ABI from a plain C99 host: tests/c/blob_host_check.c is compiled with gcc (-std=c99 -pedantic -Werror, so
+both headers are valid C, not just C++), linked against libb200hash.so and driven with fake transport callbacks.
+It mirrors how a cgo binding of go/blob.go's blobUpload would call the library."""
+import base64
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from modal_client_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    _lib.build_library()
+    out = str(tmp_path_factory.mktemp("c_host") / "blob_host_check")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "blob_host_check.c"), "-o", out, "-L", libdir, "-l:libb200hash.so",
+           f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+def _payload(seed: int, n: int) -> bytes:
+    i = np.arange(n, dtype=np.uint64)
+    return ((((i + np.uint64(seed)) & np.uint64(0xffffffff)) * np.uint64(2654435761) & np.uint64(0xffffffff))
+            >> np.uint64(24)).astype(np.uint8).tobytes()
+
+
+def test_blob_header_declares_what_the_library_exports():
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "b200blob.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(b200blob_[a-z0-9_]+)\s*\(", text)))
+    assert declared == ["b200blob_hashes_many", "b200blob_should_upload", "b200blob_upload", "b200blob_upload_many"]
+    lib = _lib.load_library()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_c_host_compiles_and_fails_loudly_without_gpu(exe):
+    r = subprocess.run([exe, "nogpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK nogpu" in r.stdout, r.stdout + r.stderr
+    assert "sm_100a" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_host_blob_upload_matches_hashlib(exe):
+    r = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK run" in r.stdout, r.stdout + r.stderr
+    lines = r.stdout.splitlines()
+    seen = 0
+    for ln in lines:
+        if ln.startswith("hashes "):
+            _, seed, n, md5_b64, sha_b64, _id = ln.split()
+            data = _payload(int(seed), int(n))
+            assert md5_b64 == base64.b64encode(hashlib.md5(data).digest()).decode()      # go/blob.go:51,53
+            assert sha_b64 == base64.b64encode(hashlib.sha256(data).digest()).decode()   # go/blob.go:52,54
+            seen += 1
+    assert seen == 8 + 9
+    text = r.stdout
+    assert "multipart_error Function input size exceeds multipart upload threshold, unsupported by this SDK version" in text
+    assert "no_url_error missing upload URL in BlobCreate response" in text
+    assert "create_error failed to create blob: rpc unavailable" in text
+    assert "put_error failed blob upload: 500" in text
+    launches = int(re.search(r"many_launches (\d+)", text).group(1))
+    assert launches <= 4  # 300 payloads: one batch (plan kernels + one lane_hash launch), not 300 hash calls
