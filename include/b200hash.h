@@ -139,6 +139,9 @@ int b200h_dedupe_device(b200h_ctx* ctx, const void* d_keys, uint64_t n, uint32_t
  * [start, start+nbytes) of stream `seed`; d_dst 8-byte aligned, start a multiple of 8. */
 int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64_t seed, uint64_t start,
                             void* cuda_stream);
+/* How many messages of the most recent batch the planner handed to the outlier path (chain kernel: one CTA per
+ * long message) instead of the lane kernel.  Diagnostic; synchronises the context's streams. */
+int b200h_last_outlier_count(b200h_ctx* ctx, uint32_t* count_out);
 /* Kernels launched by this context so far (all kinds). */
 uint64_t b200h_launch_count(b200h_ctx* ctx);
 /* When enabled, every lane_hash launch is bracketed by CUDA events on its stream;

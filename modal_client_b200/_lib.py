@@ -29,6 +29,7 @@ ABI_SYMBOLS = (
     "b200h_hash_fixed_parts", "b200h_stat_files", "b200h_hash_files", "b200h_stream_new", "b200h_stream_update", "b200h_stream_digest",
     "b200h_stream_reset", "b200h_stream_free", "b200h_fill_synth_device", "b200h_launch_count",
     "b200h_profile_enable", "b200h_profile_read", "b200h_dedupe_host", "b200h_dedupe_device",
+    "b200h_last_outlier_count",
 )
 
 
@@ -109,6 +110,8 @@ def load_library() -> ctypes.CDLL:
         L.b200h_profile_enable.restype = i32
         L.b200h_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
         L.b200h_profile_read.restype = i32
+        L.b200h_last_outlier_count.argtypes = [vp, ctypes.POINTER(u32)]
+        L.b200h_last_outlier_count.restype = i32
         L.b200h_dedupe_host.argtypes = [vp, vp, u64, u32, vp, ctypes.POINTER(u64)]
         L.b200h_dedupe_host.restype = i32
         L.b200h_dedupe_device.argtypes = [vp, vp, u64, u32, vp, vp, vp]
@@ -161,6 +164,13 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._L.b200h_launch_count(self._h))
+
+    @property
+    def last_outlier_count(self) -> int:
+        """Messages of the most recent batch that went to the outlier (chain) kernel; synchronises."""
+        c = ctypes.c_uint32()
+        self._check(self._L.b200h_last_outlier_count(self._h, ctypes.byref(c)), "b200h_last_outlier_count")
+        return int(c.value)
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.b200h_profile_enable(self._h, int(on)), "b200h_profile_enable")

@@ -62,11 +62,12 @@ struct b200h_ctx {
     std::string err;
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_chain = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    // The warp-specialised chain kernel (TMA tiles + mbarriers) is OFF by default: measured on B200 it loses to
-    // the lane kernel with packed lanes in every configuration tried (profiles/r1_chain_vs_lane.md) because a
-    // lone warp issues only ~0.27 IPC whatever it runs.  B200H_CHAIN=N (N>=1) routes up to N outliers to it.
-    bool chain_enabled = false;
-    uint32_t chain_cap = 296;
+    // Outlier path: the warp-specialised chain kernel (TMA tile ring + mbarriers; schedule expansion, SHA-256 rounds
+    // and MD5 on three warps of one CTA) runs ONE chain about twice as fast as a lane does (62 vs 30 MB/s fused),
+    // at up to 4 CTAs per SM.  The planner (plan_scan_kernel) hands it only true outliers and only when all of
+    // them fit in chain_cap CTAs; everything else stays on the lane kernel.  B200H_CHAIN=0 disables it, =N sets the cap.
+    bool chain_enabled = true;
+    uint32_t chain_cap = 592;  // 4 CTAs per SM: per-chain speed holds up to here (profiles/r1_outlier_chain.md)
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};    // H2D of a wave slot finished
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // kernels reading a wave slot finished
     cudaEvent_t ev_pin[2] = {nullptr, nullptr};       // H2D out of a pinned slot finished
@@ -226,7 +227,7 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
         CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_chain, ctx->ev_fork, 0));
         ctx->launches += launch_chain_hash(d_base, d_off, len_used, chain_list, qctl, kflags, d_sha, d_md5, states,
-                                           resume, ctx->s_chain);
+                                           resume, ctx->chain_cap, ctx->s_chain);
         CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->s_chain));
     }
     cudaEvent_t pa, pb;
@@ -614,7 +615,7 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
     }
     CU_INIT(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU_INIT(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    if (const char* e = getenv("B200H_CHAIN")) {  // tuning knob: 0 disables, N caps the chain-kernel share
+    if (const char* e = getenv("B200H_CHAIN")) {  // tuning knob: 0 disables the outlier path, N >= 2 sets the CTA cap
         const long v = atol(e);
         ctx->chain_enabled = v > 0;
         if (v > 1) ctx->chain_cap = (uint32_t)std::min<long>(v, (long)kMaxChain);
@@ -990,6 +991,19 @@ int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->s_comp;
     ctx->launches += launch_fill_synth((uint8_t*)d_dst, nbytes, seed, start, st);
     CU_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+int b200h_last_outlier_count(b200h_ctx* ctx, uint32_t* count_out) {
+    if (!ctx || !count_out) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *count_out = 0;
+    if (!ctx->d_scratch.p) return 0;  // no batch yet
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaDeviceSynchronize());
+    int q[4] = {0, 0, 0, 0};
+    CU_TRY(ctx, cudaMemcpy(q, plan_qctl((uint32_t*)ctx->d_scratch.p), sizeof q, cudaMemcpyDeviceToHost));
+    *count_out = (uint32_t)q[3];
     return 0;
 }
 

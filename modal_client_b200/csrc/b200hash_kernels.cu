@@ -10,8 +10,9 @@
 //                      its own 128-byte chunks with cp.async (LDGSTS) into a private, conflict-free
 //                      shared-memory slot, double buffered, and runs both compression functions interleaved
 //                      in registers.  Bound: INT32 issue (ALU pipe for SHF/LOP3/PRMT, FMA pipe for the adds).
-//   chain_hash_kernel  opt-in (B200H_CHAIN): CTA per long message, TMA bulk tiles (UBLKCP) + mbarrier ring,
-//                      32-lane schedule expansion, SHA and MD5 chains on separate warps.
+//   chain_hash_kernel  outlier path: CTA per long message, TMA bulk tiles (UBLKCP) + mbarrier ring, 32-lane
+//                      schedule expansion, SHA-256 rounds and MD5 on separate warps: one chain at the one-warp
+//                      issue limit (0.5 instr/clk over 1 056 instead of 2 108 instructions per block), ~2x a lane.
 //   trim_kernel        warp per message reverse scan for the last non-zero byte (HBM bound).
 //   plan kernels       bucket messages by block count (longest first) straight into the work queue.
 //   fill_synth_kernel  counter-based synthetic bytes (bench/test data; same stream as synth.py).
@@ -1079,6 +1080,7 @@ __device__ __forceinline__ uint32_t plan_bucket(uint64_t len) {
 __device__ __forceinline__ uint64_t plan_bucket_min_blocks(uint32_t b) {
     if (b < 16) return b;
     const uint32_t e = (b - 16) / 8 + 4, mant = (b - 16) % 8;
+    if (e - 3 >= 60) return ~0ull;  // buckets no 64-bit length can reach: saturate instead of wrapping around
     return (uint64_t)(8 + mant) << (e - 3);
 }
 
@@ -1105,16 +1107,28 @@ __global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, u
 // hist[0..B) counts -> cursor[0..B) start positions, longest bucket first; also decides how many of the
 // longest messages leave the lane queue for the chain kernel.  Single CTA of kPlanBuckets threads.
 //
-// Chain selection: a message is an outlier when hashing it on one lane (~29 MB/s) would outlast the whole
-// batch on the lane kernel (~700 GB/s), i.e. when its block count exceeds total_blocks / kChainRatio; it must
-// also be long enough (kChainMinBlocks) for the tile pipeline to pay off.  At most max_chain messages (the
-// longest) are taken.  qctl = {lane entries available, head, tail, chain count}.
+// Chain selection.  One chain on the chain kernel runs ~2x faster than on a lane (62 vs 30 MB/s fused, the
+// one-warp issue limit of 0.5 instr/clk applied to 1 056 instead of 2 108 instructions per block), but a chain CTA
+// serves ONE message with three warps where a lane-kernel warp serves 32, and the two kernels slow each other
+// down while they share SMSPs.  So only true outliers go there -- the messages that would still be running on
+// their lane after everything else has finished:
+//   (1) longer than the whole batch takes on the saturated lane kernel (block count > total_blocks / kChainRatio)
+//       and long enough for the tile pipeline to pay off (kChainMinBlocks);
+//   (2) longer than half the longest message (anything shorter finishes on a lane before the longest one
+//       finishes on the chain kernel);
+//   (3) and only if ALL such messages fit (count <= max_chain, one CTA per SM): routing a part of a set of
+//       equally long messages leaves the makespan where it was and costs the interference (measured: 2048 x 4 MiB
+//       159 -> 332 ms with 148 of them moved over).
+// qctl = {lane entries available, head, tail, chain count}.
 __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, int* __restrict__ qctl,
                                  const unsigned long long* __restrict__ total_blocks, uint32_t n, uint32_t max_chain) {
     __shared__ uint32_t sh[kPlanBuckets];
-    __shared__ uint32_t sh_chain;
+    __shared__ uint32_t sh_chain, sh_top;
     const int t = threadIdx.x;
-    if (t == 0) sh_chain = 0;
+    if (t == 0) {
+        sh_chain = 0;
+        sh_top = 0;
+    }
     const int rev = kPlanBuckets - 1 - t;  // position in longest-first order
     sh[t] = hist[rev];
     __syncthreads();
@@ -1127,12 +1141,17 @@ __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __
     cursor[rev] = sh[t] - hist[rev];  // exclusive
     unsigned long long thr = *total_blocks / kChainRatio;
     if (thr < kChainMinBlocks) thr = kChainMinBlocks;
+    // longest non-empty bucket -> rule (2); buckets are 12.5 % wide, compare on their lower bounds
+    if (hist[rev]) atomicMax(&sh_top, (uint32_t)rev);
+    __syncthreads();
+    const unsigned long long half = plan_bucket_min_blocks(sh_top) / 2;
+    if (thr < half) thr = half;
     const bool mine = plan_bucket_min_blocks((uint32_t)rev) >= thr;
     const bool next = rev > 0 && plan_bucket_min_blocks((uint32_t)rev - 1) >= thr;
-    if (mine && !next) sh_chain = sh[t];  // inclusive count of everything at least this long
+    if (mine && !next) atomicMax(&sh_chain, sh[t]);  // inclusive count of everything at least this long
     __syncthreads();
     if (t == 0) {
-        const uint32_t c = sh_chain < max_chain ? sh_chain : max_chain;
+        const uint32_t c = sh_chain <= max_chain ? sh_chain : 0u;  // rule (3): all of them or none
         qctl[0] = (int)(n - c);  // lane-queue entries available
         qctl[1] = 0;             // head ticket
         qctl[2] = (int)(n - c);  // tail ticket
@@ -1236,9 +1255,10 @@ int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* chain
 // on the device, in qctl[3]).
 int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* chain_list,
                       const int* qctl, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
-                      bool resume, cudaStream_t st) {
+                      bool resume, uint32_t max_chain, cudaStream_t st) {
     const bool s = flags & F_SHA256, m = flags & F_MD5;
-    const int grid = (int)kMaxChain;
+    const int grid = (int)(max_chain < kMaxChain ? max_chain : kMaxChain);
+    if (grid <= 0) return 0;
     if (s && m)
         chain_hash_kernel<true, true><<<grid, kChainThreads, kChainSmem, st>>>(base, off, len, chain_list, qctl, flags,
                                                                                sha_out, md5_out, state, resume, 1u);

@@ -37,7 +37,7 @@ int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring /*ring_capacity(
                 uint32_t* scratch /*kPlanScratchWords*/, bool fresh, uint32_t max_chain, cudaStream_t st);
 int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* chain_list,
                       const int* qctl, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
-                      bool resume, cudaStream_t st);
+                      bool resume, uint32_t max_chain /*grid: one CTA per possible entry*/, cudaStream_t st);
 int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring, int* qctl,
                      uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out,
                      ChainState* state /*n entries: caller states (F_NO_FINAL / resume) or scratch*/, cudaStream_t st);

@@ -422,3 +422,27 @@ def test_dedupe_million_rows_and_device_entry_point(ctx):
     assert np.array_equal(d_first.cpu().numpy().view(np.uint32), want) and int(d_nd.item()) == want_nd
     with pytest.raises(_lib.B200HashError):
         ctx.dedupe_device(d_keys.data_ptr(), 10, 24, d_first.data_ptr())  # unsupported key width
+
+
+def test_outlier_routing_policy(ctx):
+    """The planner sends true outliers -- and only those -- to the chain kernel (regression test: an overflow in
+    the bucket bounds once made it route nothing at all).  Digests are checked in every case."""
+    import torch
+
+    def run(lens, flags=BOTH):
+        lens = np.asarray(lens, np.uint64)
+        offs = np.concatenate([[0], np.cumsum(lens + np.uint64(7))])[:-1].astype(np.uint64)
+        buf = synth_array(23, int(offs[-1] + lens[-1]) + 8)
+        sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, flags)
+        routed = ctx.last_outlier_count
+        s, m, _ = c_oracle.hash_batch(buf, offs, lens, sha=bool(flags & _lib.SHA256), md5=bool(flags & _lib.MD5))
+        assert (s is None or np.array_equal(sha, s)) and (m is None or np.array_equal(md5, m))
+        return routed
+
+    assert run([3 << 20] + [5000] * 3000) == 1                     # one long file in a tree of small ones
+    assert run([3 << 20, (3 << 20) - 4097, 1 << 20] + [70_000] * 500) == 2   # the 1 MiB one is < half the longest
+    assert run([1 << 20] * 40, _lib.SHA256) == 40                  # few equally long messages: all of them fit
+    assert run([100_000] * 2000) == 0                              # nothing stands out (one staging wave)
+    assert run([80 * 1024] * 700) == 0                             # more equally long messages than chain CTAs
+    assert run([2 << 20]) == 1 and run([100]) == 0 and run([0]) == 0
+    torch.cuda.synchronize()

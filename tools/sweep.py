@@ -48,7 +48,7 @@ def run(name, offs, lens, flags, reps=3, **extra):
 BOTH = _lib.SHA256 | _lib.MD5
 which = sys.argv[1:] or ["c5", "c4", "c3"]
 if "c5" in which:
-    for k in range(0, 10):
+    for k in range(0, int(os.environ.get("B200H_SWEEP_KMAX", 9)) + 1):
         size = 4096 * 4**k
         n = max(2, CAP // size)
         if size * n > CAP:
