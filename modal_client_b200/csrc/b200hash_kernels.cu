@@ -780,13 +780,118 @@ __device__ __forceinline__ void load_block_words(const uint8_t* blk, uint32_t to
     }
 }
 
-#define CH_RND(a, b, c, d, e, f, g, h, WK)                                            \
+// One SHA-256 round for the chain warp.  A lone warp issues at most one instruction every two cycles whatever
+// the pipe, so what counts here is the instruction count: the two three-input sums are IADD3s (14 instructions
+// per round instead of 16 with two-input IMAD adds: 2 049 -> 1 769 cycles per block, tools/chainbench.cu).
+#define CH_RND_FMA(a, b, c, d, e, f, g, h, WK)                                        \
     {                                                                                 \
         uint32_t t1 = ADD(ADD(ADD(h, WK), lop3<0xCA>(e, f, g)), SHA_S1(e));           \
         uint32_t t2 = ADD(SHA_S0(a), lop3<0xE8>(a, b, c));                            \
         d = ADD(d, t1);                                                               \
         h = ADD(t1, t2);                                                              \
     }
+#define CH_RND(a, b, c, d, e, f, g, h, WK)                                            \
+    {                                                                                 \
+        const uint32_t hwk = ADD(h, WK);                                              \
+        const uint32_t t1 = hwk + lop3<0xCA>(e, f, g) + SHA_S1(e);                    \
+        d = ADD(d, t1);                                                               \
+        h = t1 + SHA_S0(a) + lop3<0xE8>(a, b, c);                                     \
+    }
+
+// MD5 block for the chain warp.  One chain on one warp is bound by the dependent-instruction latency of a step
+// (b -> F -> sum -> rotate -> + b), not by issue slots, so the step is written for the shortest dependency chain:
+// (x + T) off the critical path, one IADD3, and rotate+add left to ptxas as a single LEA.HI:
+// 1 204 -> 816 cycles per block (104 -> 154 MB/s, tools/chainbench.cu).
+// T[i] = floor(2^32 * |sin(i + 1)|) (RFC 1321); a switch so that the unrolled steps get immediates, not
+// constant-bank loads whose latency a lone warp cannot hide.
+__device__ __forceinline__ constexpr uint32_t md5_T(int i) {
+    switch (i) {
+        case 0: return 0xd76aa478u;
+        case 1: return 0xe8c7b756u;
+        case 2: return 0x242070dbu;
+        case 3: return 0xc1bdceeeu;
+        case 4: return 0xf57c0fafu;
+        case 5: return 0x4787c62au;
+        case 6: return 0xa8304613u;
+        case 7: return 0xfd469501u;
+        case 8: return 0x698098d8u;
+        case 9: return 0x8b44f7afu;
+        case 10: return 0xffff5bb1u;
+        case 11: return 0x895cd7beu;
+        case 12: return 0x6b901122u;
+        case 13: return 0xfd987193u;
+        case 14: return 0xa679438eu;
+        case 15: return 0x49b40821u;
+        case 16: return 0xf61e2562u;
+        case 17: return 0xc040b340u;
+        case 18: return 0x265e5a51u;
+        case 19: return 0xe9b6c7aau;
+        case 20: return 0xd62f105du;
+        case 21: return 0x02441453u;
+        case 22: return 0xd8a1e681u;
+        case 23: return 0xe7d3fbc8u;
+        case 24: return 0x21e1cde6u;
+        case 25: return 0xc33707d6u;
+        case 26: return 0xf4d50d87u;
+        case 27: return 0x455a14edu;
+        case 28: return 0xa9e3e905u;
+        case 29: return 0xfcefa3f8u;
+        case 30: return 0x676f02d9u;
+        case 31: return 0x8d2a4c8au;
+        case 32: return 0xfffa3942u;
+        case 33: return 0x8771f681u;
+        case 34: return 0x6d9d6122u;
+        case 35: return 0xfde5380cu;
+        case 36: return 0xa4beea44u;
+        case 37: return 0x4bdecfa9u;
+        case 38: return 0xf6bb4b60u;
+        case 39: return 0xbebfbc70u;
+        case 40: return 0x289b7ec6u;
+        case 41: return 0xeaa127fau;
+        case 42: return 0xd4ef3085u;
+        case 43: return 0x04881d05u;
+        case 44: return 0xd9d4d039u;
+        case 45: return 0xe6db99e5u;
+        case 46: return 0x1fa27cf8u;
+        case 47: return 0xc4ac5665u;
+        case 48: return 0xf4292244u;
+        case 49: return 0x432aff97u;
+        case 50: return 0xab9423a7u;
+        case 51: return 0xfc93a039u;
+        case 52: return 0x655b59c3u;
+        case 53: return 0x8f0ccc92u;
+        case 54: return 0xffeff47du;
+        case 55: return 0x85845dd1u;
+        case 56: return 0x6fa87e4fu;
+        case 57: return 0xfe2ce6e0u;
+        case 58: return 0xa3014314u;
+        case 59: return 0x4e0811a1u;
+        case 60: return 0xf7537e82u;
+        case 61: return 0xbd3af235u;
+        case 62: return 0x2ad7d2bbu;
+        default: return 0xeb86d391u;
+    }
+}
+
+__device__ __forceinline__ void md5_chain_block(uint32_t (&hm)[4], const uint32_t (&x)[16]) {
+    uint32_t v[4] = {hm[0], hm[1], hm[2], hm[3]};  // A B C D; step i writes v[(64 - i) & 3] (RFC 1321 role rotation)
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        const int r = i >> 4;
+        const int g = r == 0 ? i : r == 1 ? (5 * i + 1) & 15 : r == 2 ? (3 * i + 5) & 15 : (7 * i) & 15;
+        const int sh = r == 0 ? (i & 3) * 5 + 7                                   // 7 12 17 22
+                              : r == 1 ? ((i & 3) == 0 ? 5 : (i & 3) == 1 ? 9 : (i & 3) == 2 ? 14 : 20)
+                                       : r == 2 ? ((i & 3) == 0 ? 4 : (i & 3) == 1 ? 11 : (i & 3) == 2 ? 16 : 23)
+                                                : ((i & 3) == 0 ? 6 : (i & 3) == 1 ? 10 : (i & 3) == 2 ? 15 : 21);
+        uint32_t& a = v[(64 - i) & 3];
+        const uint32_t b = v[(65 - i) & 3], c = v[(66 - i) & 3], d = v[(67 - i) & 3];
+        const uint32_t fn = r == 0 ? lop3<0xCA>(b, c, d) : r == 1 ? lop3<0xE4>(b, c, d)
+                                   : r == 2 ? lop3<0x96>(b, c, d) : lop3<0x39>(b, c, d);
+        const uint32_t xt = x[g] + md5_T(i);
+        a = b + rotl(a + fn + xt, sh);
+    }
+    hm[0] += v[0]; hm[1] += v[1]; hm[2] += v[2]; hm[3] += v[3];
+}
 
 template <bool DO_SHA, bool DO_MD5>
 __global__ void __launch_bounds__(kChainThreads)
@@ -967,7 +1072,6 @@ chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
         // ----------------------------------------------------------------------------------- MD5 chain
         if (!DO_MD5) return;
         uint32_t hm[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
-        uint32_t unused[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (resume && lane == 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) hm[i] = st[mi].md5[i];
@@ -982,7 +1086,7 @@ chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
                 for (uint32_t bidx = 0; bidx < nb; ++bidx) {
                     uint32_t x[16];
                     load_block_words(tiles + slot * kTileStride + bidx * 64, toff, x);
-                    compress<false, true>(unused, hm, x, false, 0u, 0u, one);
+                    md5_chain_block(hm, x);
                 }
             }
             __syncwarp();

@@ -8,6 +8,45 @@
 
 namespace b200h {
 
+// round variants for the lone-warp chain: fewer instructions matter more than pipe placement at 0.5 instr/clk
+#define CH_RND_PLAIN(a, b, c, d, e, f, g, h, WK)                                      \
+    {                                                                                 \
+        const uint32_t t1 = h + WK + lop3<0xCA>(e, f, g) + SHA_S1(e);                 \
+        d += t1;                                                                      \
+        h = t1 + SHA_S0(a) + lop3<0xE8>(a, b, c);                                     \
+    }
+#define CH_RND_DPRE(a, b, c, d, e, f, g, h, WK)                                       \
+    {                                                                                 \
+        const uint32_t hwk = ADD(h, WK);                                              \
+        const uint32_t dh = ADD(d, hwk);                                              \
+        const uint32_t cs = lop3<0xCA>(e, f, g) + SHA_S1(e);                          \
+        d = ADD(dh, cs);                                                              \
+        h = hwk + cs + SHA_S0(a) + lop3<0xE8>(a, b, c);                               \
+    }
+
+// MD5 block for the lone-warp chain, step written so that ptxas fuses rotate+add into LEA.HI (VAR 1) or with the
+// shipped MD5_STEP_MIX form (VAR 0): latency, not instruction count, bounds this chain.
+template <int VAR>
+__device__ __forceinline__ void md5_block_xt(uint32_t (&hm)[4], const uint32_t (&xt)[64], uint32_t one) {
+    // xt[i] = M[g(i)] + T[i] prepared by another warp (like W+K for SHA-256)
+    constexpr int S[4][4] = {{7, 12, 17, 22}, {5, 9, 14, 20}, {4, 11, 16, 23}, {6, 10, 15, 21}};
+    uint32_t v[4] = {hm[0], hm[1], hm[2], hm[3]};  // a b c d
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        const int r = i >> 4;
+        // roles rotate: step i updates v[(4 - i) & 3] using the other three in order
+        uint32_t& a = v[(64 - i) & 3];
+        const uint32_t b = v[(65 - i) & 3], c = v[(66 - i) & 3], d = v[(67 - i) & 3];
+        const uint32_t fn = r == 0 ? lop3<0xCA>(b, c, d) : r == 1 ? lop3<0xE4>(b, c, d) : r == 2 ? lop3<0x96>(b, c, d) : lop3<0x39>(b, c, d);
+        if (VAR == 1) {
+            a = b + rotl(a + fn + xt[i], S[r][i & 3]);                    // IADD3 + LEA.HI
+        } else {
+            a = addf(b, rotl(a + fn + xt[i], S[r][i & 3]), one);          // IADD3 + SHF + IMAD
+        }
+    }
+    hm[0] += v[0]; hm[1] += v[1]; hm[2] += v[2]; hm[3] += v[3];
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128) chain_bench(uint32_t* out, long long* cyc, int nblocks, uint32_t one, uint32_t seed) {
     __shared__ __align__(16) uint32_t rows[32][68];  // 32 blocks of 64 W+K words (or 16 message words), padded
@@ -19,7 +58,15 @@ __global__ void __launch_bounds__(128) chain_bench(uint32_t* out, long long* cyc
 #pragma unroll 1
     for (int b = 0; b < nblocks; ++b) {
         const uint4* row = reinterpret_cast<const uint4*>(rows[b & 31]);
-        if (MODE == 0) {
+        if (MODE == 7 || MODE == 8) {
+            uint32_t xt[64];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint4 v = row[i];
+                xt[4 * i] = v.x; xt[4 * i + 1] = v.y; xt[4 * i + 2] = v.z; xt[4 * i + 3] = v.w;
+            }
+            md5_block_xt<MODE == 7 ? 1 : 0>(hm, xt, one);
+        } else if (MODE == 0 || MODE >= 4) {
             uint32_t k[64];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -27,17 +74,17 @@ __global__ void __launch_bounds__(128) chain_bench(uint32_t* out, long long* cyc
                 k[4 * i] = v.x; k[4 * i + 1] = v.y; k[4 * i + 2] = v.z; k[4 * i + 3] = v.w;
             }
             uint32_t a = hs[0], bb = hs[1], c = hs[2], d = hs[3], e = hs[4], f = hs[5], g = hs[6], h = hs[7];
-#pragma unroll
-            for (int i = 0; i < 64; i += 8) {
-                CH_RND(a, bb, c, d, e, f, g, h, k[i]);
-                CH_RND(h, a, bb, c, d, e, f, g, k[i + 1]);
-                CH_RND(g, h, a, bb, c, d, e, f, k[i + 2]);
-                CH_RND(f, g, h, a, bb, c, d, e, k[i + 3]);
-                CH_RND(e, f, g, h, a, bb, c, d, k[i + 4]);
-                CH_RND(d, e, f, g, h, a, bb, c, k[i + 5]);
-                CH_RND(c, d, e, f, g, h, a, bb, k[i + 6]);
-                CH_RND(bb, c, d, e, f, g, h, a, k[i + 7]);
-            }
+#define R8(RND)                                                                              \
+    _Pragma("unroll") for (int i = 0; i < 64; i += 8) {                                      \
+        RND(a, bb, c, d, e, f, g, h, k[i]);     RND(h, a, bb, c, d, e, f, g, k[i + 1]);      \
+        RND(g, h, a, bb, c, d, e, f, k[i + 2]); RND(f, g, h, a, bb, c, d, e, k[i + 3]);      \
+        RND(e, f, g, h, a, bb, c, d, k[i + 4]); RND(d, e, f, g, h, a, bb, c, k[i + 5]);      \
+        RND(c, d, e, f, g, h, a, bb, k[i + 6]); RND(bb, c, d, e, f, g, h, a, k[i + 7]);      \
+    }
+            if (MODE == 0) { R8(CH_RND_FMA) }
+            if (MODE == 4) { R8(CH_RND) }
+            if (MODE == 5) { R8(CH_RND_PLAIN) }
+            if (MODE == 6) { R8(CH_RND_DPRE) }
             hs[0] += a; hs[1] += bb; hs[2] += c; hs[3] += d; hs[4] += e; hs[5] += f; hs[6] += g; hs[7] += h;
         } else {
             uint32_t x[16];
@@ -46,6 +93,7 @@ __global__ void __launch_bounds__(128) chain_bench(uint32_t* out, long long* cyc
                 const uint4 v = row[i];
                 x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
             }
+            if (MODE == 9) md5_chain_block(hm, x);
             if (MODE == 1) compress<true, false>(hs, hm, x, false, 0u, 0u, one);
             if (MODE == 2) compress<false, true>(hs, hm, x, false, 0u, 0u, one);
             if (MODE == 3) compress<true, true>(hs, hm, x, false, 0u, 0u, one);
@@ -83,8 +131,14 @@ static void run(const char* name, int warps) {
 }
 
 int main() {
-    for (int w : {1, 2, 4}) {
-        run<0>("SHA-256 rounds only (W+K from smem)", w);
+    run<4>("rounds only (shipped: 2 IADD3)", 1);
+    run<5>("rounds only, plain C adds", 1);
+    run<6>("rounds only, d pre-added", 1);
+    run<7>("MD5 from M+T rows, IADD3 + LEA.HI", 1);
+    run<8>("MD5 from M+T rows, IADD3 + SHF + IMAD", 1);
+    run<9>("MD5 md5_chain_block (shipped)", 1);
+    for (int w : {1, 4}) {
+        run<0>("rounds only, all adds IMAD", w);
         run<1>("SHA-256 full (schedule + rounds)", w);
         run<2>("MD5", w);
         run<3>("fused SHA-256 + MD5", w);
