@@ -873,7 +873,7 @@ __device__ __forceinline__ constexpr uint32_t md5_T(int i) {
     }
 }
 
-__device__ __forceinline__ void md5_chain_block(uint32_t (&hm)[4], const uint32_t (&x)[16]) {
+__device__ __forceinline__ void md5_chain_block(uint32_t (&hm)[4], const uint32_t (&x)[16], uint32_t one) {
     uint32_t v[4] = {hm[0], hm[1], hm[2], hm[3]};  // A B C D; step i writes v[(64 - i) & 3] (RFC 1321 role rotation)
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
@@ -887,7 +887,9 @@ __device__ __forceinline__ void md5_chain_block(uint32_t (&hm)[4], const uint32_
         const uint32_t b = v[(65 - i) & 3], c = v[(66 - i) & 3], d = v[(67 - i) & 3];
         const uint32_t fn = r == 0 ? lop3<0xCA>(b, c, d) : r == 1 ? lop3<0xE4>(b, c, d)
                                    : r == 2 ? lop3<0x96>(b, c, d) : lop3<0x39>(b, c, d);
-        const uint32_t xt = x[g] + md5_T(i);
+        // x + T as a multiply-add by the run-time 1: ptxas cannot re-associate through it (with a plain add it
+        // folds T into IADD3(F, T, x) and appends "+ a", one more dependent instruction per step)
+        const uint32_t xt = addf(x[g], md5_T(i), one);
         a = b + rotl(a + fn + xt, sh);
     }
     hm[0] += v[0]; hm[1] += v[1]; hm[2] += v[2]; hm[3] += v[3];
@@ -1086,7 +1088,7 @@ chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
                 for (uint32_t bidx = 0; bidx < nb; ++bidx) {
                     uint32_t x[16];
                     load_block_words(tiles + slot * kTileStride + bidx * 64, toff, x);
-                    md5_chain_block(hm, x);
+                    md5_chain_block(hm, x, one);
                 }
             }
             __syncwarp();

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) chain_bench(uint32_t* out, long long* cyc
                 xt[4 * i] = v.x; xt[4 * i + 1] = v.y; xt[4 * i + 2] = v.z; xt[4 * i + 3] = v.w;
             }
             md5_block_xt<MODE == 7 ? 1 : 0>(hm, xt, one);
-        } else if (MODE == 0 || MODE >= 4) {
+        } else if (MODE == 0 || (MODE >= 4 && MODE <= 6)) {
             uint32_t k[64];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) chain_bench(uint32_t* out, long long* cyc
                 const uint4 v = row[i];
                 x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
             }
-            if (MODE == 9) md5_chain_block(hm, x);
+            if (MODE == 9) md5_chain_block(hm, x, one);
             if (MODE == 1) compress<true, false>(hs, hm, x, false, 0u, 0u, one);
             if (MODE == 2) compress<false, true>(hs, hm, x, false, 0u, 0u, one);
             if (MODE == 3) compress<true, true>(hs, hm, x, false, 0u, 0u, one);
