@@ -73,7 +73,8 @@ int b200h_hash_batch_host(b200h_ctx* ctx, const uint8_t* base, const uint64_t* o
 
 /* Same, but every pointer is a DEVICE pointer on ctx's device and the call only enqueues work on
  * `cuda_stream` (a cudaStream_t; NULL = the context's compute stream).  d_sha256/d_md5 must be 16-byte
- * aligned.  This is the HBM-resident path the roofline is quoted on. */
+ * aligned.  This is the HBM-resident path the roofline is quoted on.  (The call synchronises `cuda_stream` once,
+ * briefly, after the ~12 us planning kernels, to read how many outlier messages go to the chain kernel.) */
 int b200h_hash_batch_device(b200h_ctx* ctx, const void* d_base, const uint64_t* d_offsets, const uint64_t* d_lengths,
                             uint64_t n, uint32_t flags, void* d_sha256, void* d_md5, uint64_t* d_trimmed_len,
                             void* cuda_stream);
@@ -140,7 +141,7 @@ int b200h_dedupe_device(b200h_ctx* ctx, const void* d_keys, uint64_t n, uint32_t
 int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64_t seed, uint64_t start,
                             void* cuda_stream);
 /* How many messages of the most recent batch the planner handed to the outlier path (chain kernel: one CTA per
- * long message) instead of the lane kernel.  Diagnostic; synchronises the context's streams. */
+ * long message) instead of the lane kernel.  Diagnostic. */
 int b200h_last_outlier_count(b200h_ctx* ctx, uint32_t* count_out);
 /* Kernels launched by this context so far (all kinds). */
 uint64_t b200h_launch_count(b200h_ctx* ctx);

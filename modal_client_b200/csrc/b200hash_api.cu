@@ -67,7 +67,10 @@ struct b200h_ctx {
     // at up to 4 CTAs per SM.  The planner (plan_scan_kernel) hands it only true outliers and only when all of
     // them fit in chain_cap CTAs; everything else stays on the lane kernel.  B200H_CHAIN=0 disables it, =N sets the cap.
     bool chain_enabled = true;
-    uint32_t chain_cap = 592;  // 4 CTAs per SM: per-chain speed holds up to here (profiles/r1_outlier_chain.md)
+    // One chain CTA per SM, each hosting up to chain_groups_per_cta() messages (set from the SM count at create).
+    uint32_t chain_cap = 592;
+    int* h_plan = nullptr;        // pinned: the planner's control block {avail, head, tail, outliers} of the last batch
+    uint32_t last_outliers = 0;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};    // H2D of a wave slot finished
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // kernels reading a wave slot finished
     cudaEvent_t ev_pin[2] = {nullptr, nullptr};       // H2D out of a pinned slot finished
@@ -222,19 +225,30 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     const bool resume = d_state != nullptr;
     ctx->launches += launch_plan(len_used, n, ring, chain_list, scratch, /*fresh=*/!resume,
                                  ctx->chain_enabled ? ctx->chain_cap : 0u, st);
+    // How many outliers did the planner pick?  The count is read back (16 bytes, one stream synchronisation after
+    // the ~12 us plan kernels) because a chain kernel launched "just in case" is not free: its CTAs ask for half an
+    // SM's shared memory and, idle or not, skew where the lane kernel's CTAs land (1 024 x 8 MiB: 260 -> 937 ms,
+    // 2 048 x 4 MiB: 159 -> 280 ms measured with a speculative launch before / after the lane kernel).
+    uint32_t n_chain = 0;
     if (ctx->chain_enabled) {
-        // outlier (long) messages run on the warp-specialised chain kernel, concurrently with the lane kernel
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, qctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        n_chain = (uint32_t)ctx->h_plan[3];
+    }
+    ctx->last_outliers = n_chain;
+    if (n_chain) {
+        // the outliers set the makespan: their CTAs go first (high-priority stream), one per SM
         CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_chain, ctx->ev_fork, 0));
         ctx->launches += launch_chain_hash(d_base, d_off, len_used, chain_list, qctl, kflags, d_sha, d_md5, states,
-                                           resume, ctx->chain_cap, ctx->s_chain);
+                                           resume, n_chain, ctx->s_chain);
         CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->s_chain));
     }
     cudaEvent_t pa, pb;
     if (int rc = prof_begin(ctx, st, &pa, &pb)) return rc;
     ctx->launches += launch_lane_hash(d_base, d_off, len_used, ring, qctl, n, kflags, d_sha, d_md5, states, st);
     if (int rc = prof_end(ctx, st, pa, pb)) return rc;
-    if (ctx->chain_enabled) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (n_chain) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaEventRecord(ctx->ev_scratch, st));
     ctx->scratch_used = true;
@@ -606,6 +620,7 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
         return bail(B200H_E_CUDA);
     }
     CU_INIT(configure_kernels());
+    ctx->chain_cap = (uint32_t)std::min<long>((long)prop.multiProcessorCount * chain_groups_per_cta(), (long)kMaxChain);
     CU_INIT(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
     CU_INIT(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
     {
@@ -613,12 +628,13 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
         CU_INIT(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU_INIT(cudaStreamCreateWithPriority(&ctx->s_chain, cudaStreamNonBlocking, hi));
     }
+    CU_INIT(cudaHostAlloc(&ctx->h_plan, 64, cudaHostAllocDefault));
     CU_INIT(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU_INIT(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     if (const char* e = getenv("B200H_CHAIN")) {  // tuning knob: 0 disables the outlier path, N >= 2 sets the CTA cap
         const long v = atol(e);
         ctx->chain_enabled = v > 0;
-        if (v > 1) ctx->chain_cap = (uint32_t)std::min<long>(v, (long)kMaxChain);
+        if (v > 1) ctx->chain_cap = (uint32_t)std::min<long>(v, (long)ctx->chain_cap);  // never above groups x SMs
     }
     for (int s = 0; s < 2; ++s) {
         CU_INIT(cudaEventCreateWithFlags(&ctx->ev_copied[s], cudaEventDisableTiming));
@@ -663,6 +679,7 @@ void b200h_destroy(b200h_ctx* ctx) {
     if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
     if (ctx->ev_dedupe) cudaEventDestroy(ctx->ev_dedupe);
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
+    if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_chain) cudaStreamDestroy(ctx->s_chain);
@@ -997,13 +1014,7 @@ int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64
 int b200h_last_outlier_count(b200h_ctx* ctx, uint32_t* count_out) {
     if (!ctx || !count_out) return B200H_E_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    *count_out = 0;
-    if (!ctx->d_scratch.p) return 0;  // no batch yet
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
-    CU_TRY(ctx, cudaDeviceSynchronize());
-    int q[4] = {0, 0, 0, 0};
-    CU_TRY(ctx, cudaMemcpy(q, plan_qctl((uint32_t*)ctx->d_scratch.p), sizeof q, cudaMemcpyDeviceToHost));
-    *count_out = (uint32_t)q[3];
+    *count_out = ctx->last_outliers;
     return 0;
 }
 

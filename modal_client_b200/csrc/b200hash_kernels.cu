@@ -726,17 +726,22 @@ lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------ chain_hash_kernel
-// One CTA per (long) message, three specialised warps, tiles of 32 blocks (2 KiB):
+// One CTA per SM (its shared-memory request is more than half an SM's, so placement cannot double CTAs up); a CTA
+// hosts up to kChainGroups long messages, each served by a group of three specialised warps on tiles of 32 blocks
+// (2 KiB).  Within a group:
 //   warp 0  producer/expander: one elected lane streams the message into a 4-deep shared-memory tile ring
 //           with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP, mbarrier complete_tx); then all 32 lanes
 //           expand the SHA-256 message schedule of the tile's 32 blocks in parallel (lane = block) and store
 //           W[t]+K[t] rows for the chain warp.  The padding block(s) are synthesised into a final tile.
-//   warp 1  SHA-256 chain: one lane runs the 64 rounds per block straight from the W+K rows
-//           (10 ALU-pipe instructions per round: the serial floor of a single chain on one SMSP).
+//   warp 1  SHA-256 chain: one lane runs the 64 rounds per block straight from the W+K rows.
 //   warp 2  MD5 chain: one lane runs the 64 steps per block straight from the raw tile.
-// The three warps land on different SMSPs of the SM and hand tiles over through mbarriers only.
+// The warps of a group hand tiles over through mbarriers only.  Entry e of the chain list is served by group
+// e / gridDim.x of CTA e % gridDim.x: up to gridDim.x outliers get an SM each, and with warp w of a CTA on SMSP
+// w % 4 the twelve warps of a full CTA put exactly one expander, one SHA-256 and one MD5 warp on every SMSP.
 
-constexpr int kChainThreads = 96;
+constexpr int kChainGroups = 4;
+constexpr int kChainGroupThreads = 96;
+constexpr int kChainThreads = kChainGroupThreads * kChainGroups;
 constexpr int kTileBlocks = 32;
 constexpr int kTileData = kTileBlocks * 64;
 constexpr int kTileStride = kTileData + 32;  // + the misaligned leading granule; keeps 16-byte alignment
@@ -744,7 +749,9 @@ constexpr int kNT = 4;                        // raw tile ring depth
 constexpr int kWkRow = 64 * 4 + 16;           // 272 B: conflict-free STS.128 across lanes
 constexpr int kWkBuf = kTileBlocks * kWkRow;
 constexpr int kNW = 2;                        // W+K ring depth
-constexpr int kChainSmem = kNT * kTileStride + kNW * kWkBuf + (2 * kNT + 2 * kNW) * 8;
+constexpr int kChainGroupSmem = (kNT * kTileStride + kNW * kWkBuf + (2 * kNT + 2 * kNW) * 8 + 127) & ~127;
+constexpr int kChainSmemMin = 116 * 1024;  // > 227 KB / 2: never two chain CTAs on one SM
+constexpr int kChainSmem = kChainGroups * kChainGroupSmem > kChainSmemMin ? kChainGroups * kChainGroupSmem : kChainSmemMin;
 
 __constant__ uint32_t kShaKAll[64] = {
     0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
@@ -901,15 +908,18 @@ chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
                   const uint32_t* __restrict__ chain_list, const int* __restrict__ qctl, uint32_t flags,
                   uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out, ChainState* __restrict__ st,
                   int resume, uint32_t one) {
-    if ((int)blockIdx.x >= qctl[3]) return;
-    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t n_chain = (uint32_t)qctl[3];
+    if (blockIdx.x >= n_chain) return;  // entry e lives in CTA e % gridDim.x: this CTA has none
+    extern __shared__ __align__(128) uint8_t smem_all[];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const int grp = (threadIdx.x >> 5) / 3;   // which of the CTA's messages
+    const int warp = (threadIdx.x >> 5) % 3;  // role within the group
+    uint8_t* smem = smem_all + grp * kChainGroupSmem;
     uint8_t* tiles = smem;
     uint8_t* wkbuf = smem + kNT * kTileStride;
     const uint32_t bars = smem_u32(smem + kNT * kTileStride + kNW * kWkBuf);
     const uint32_t tile_full = bars, tile_free = bars + 8 * kNT, wk_full = bars + 16 * kNT, wk_free = bars + 16 * kNT + 8 * kNW;
-    if (threadIdx.x == 0) {
+    if (warp == 0 && lane == 0) {
         for (int i = 0; i < kNT; ++i) {
             mbar_init(tile_full + 8 * i, 1);
             mbar_init(tile_free + 8 * i, (DO_SHA ? 1 : 0) + (DO_MD5 ? 1 : 0));
@@ -922,8 +932,10 @@ chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
         fence_proxy_async();
     }
     __syncthreads();
+    const uint32_t ent = blockIdx.x + gridDim.x * (uint32_t)grp;
+    if (ent >= n_chain) return;  // this group has no message (its warps are done; the others never wait for them)
 
-    const uint32_t mi = chain_list[blockIdx.x];
+    const uint32_t mi = chain_list[ent];
     const uint8_t* p = base + off[mi];
     const uint64_t L = len[mi];
     const bool final = !(flags & F_NO_FINAL);
@@ -1361,9 +1373,11 @@ int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* chain
 // on the device, in qctl[3]).
 int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* chain_list,
                       const int* qctl, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
-                      bool resume, uint32_t max_chain, cudaStream_t st) {
+                      bool resume, uint32_t n_chain, cudaStream_t st) {
     const bool s = flags & F_SHA256, m = flags & F_MD5;
-    const int grid = (int)(max_chain < kMaxChain ? max_chain : kMaxChain);
+    // n_chain live entries (read back from the planner): entry e -> CTA e % grid, group e / grid; one CTA per SM
+    const uint32_t live = n_chain < kMaxChain ? n_chain : kMaxChain;
+    const int grid = (int)(live < (uint32_t)g_sm_count ? live : (uint32_t)g_sm_count);
     if (grid <= 0) return 0;
     if (s && m)
         chain_hash_kernel<true, true><<<grid, kChainThreads, kChainSmem, st>>>(base, off, len, chain_list, qctl, flags,
@@ -1428,6 +1442,8 @@ int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t sta
     return 1;
 }
 
+int chain_groups_per_cta() { return kChainGroups; }
+
 cudaError_t configure_kernels() {
     cudaError_t e;
     e = cudaFuncSetAttribute(lane_hash_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
@@ -1435,6 +1451,12 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(lane_hash_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lane_hash_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(chain_hash_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(chain_hash_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(chain_hash_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, ctas = 0;
     e = cudaGetDevice(&dev);

@@ -23,7 +23,7 @@ enum : uint32_t {
 constexpr int kPlanBuckets = 512;
 constexpr unsigned long long kChainMinBlocks = 1024;  // 64 KiB: shorter messages never go to the chain kernel
 constexpr unsigned long long kChainRatio = 24000;     // lane kernel ~700 GB/s vs ~29 MB/s for one lane
-constexpr uint32_t kMaxChain = 1184;                  // 8 chain CTAs per SM
+constexpr uint32_t kMaxChain = 1184;                  // chain-list capacity (entries)
 constexpr int kPlanScratchWords = 2 * kPlanBuckets + 8;  // hist, cursor, qctl[4], total_blocks (u64), pad
 
 // Launch wrappers (defined in b200hash_kernels.cu).  All asynchronous on `st`.
@@ -37,7 +37,7 @@ int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring /*ring_capacity(
                 uint32_t* scratch /*kPlanScratchWords*/, bool fresh, uint32_t max_chain, cudaStream_t st);
 int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* chain_list,
                       const int* qctl, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
-                      bool resume, uint32_t max_chain /*grid: one CTA per possible entry*/, cudaStream_t st);
+                      bool resume, uint32_t n_chain /*live entries, as read back from qctl[3]*/, cudaStream_t st);
 int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring, int* qctl,
                      uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out,
                      ChainState* state /*n entries: caller states (F_NO_FINAL / resume) or scratch*/, cudaStream_t st);
@@ -47,6 +47,7 @@ int launch_dedupe(const void* d_keys, uint64_t n, uint32_t key_bytes, uint32_t* 
                   unsigned long long* d_ndistinct, cudaStream_t st);
 int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t start, cudaStream_t st);
 
+int chain_groups_per_cta();        // long messages one chain CTA can host (one CTA per SM)
 cudaError_t configure_kernels();  // one-time cudaFuncSetAttribute calls for the current device
 const char* kernel_build_info();
 

@@ -9,3 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file
 timeout 400 ncu --set full --import-source on --clock-control none -k regex:lane_hash -s 2 -c 1 -f -o gpurun_out/prof_lane_sha_s2 python tools/kbench.py 100000 262144 1 1 > gpurun_out/ncu_sha_s2.log 2>&1
 timeout 400 ncu --set full --import-source on --clock-control none -k regex:chain_hash -s 2 -c 1 -f -o gpurun_out/prof_chain_s2 python tools/kbench.py 1 8388608 1 3 > gpurun_out/ncu_chain_s2.log 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -3
+python tools/sweep.py c4 c3 2>&1 | cut -c1-220 > gpurun_out/sweep_s2_final.jsonl
+B200H_SWEEP_KMAX=8 python tools/sweep.py c5 2>&1 | cut -c1-220 >> gpurun_out/sweep_s2_final.jsonl
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests_s2_final.txt 2>&1; tail -2 gpurun_out/gpu_tests_s2_final.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1

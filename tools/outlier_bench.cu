@@ -13,7 +13,7 @@ int main(int argc, char** argv) {
     const uint64_t n = argc > 1 ? atoll(argv[1]) : 1;
     const uint64_t size = argc > 2 ? atoll(argv[2]) : (16ull << 20);
     const uint64_t nsmall = argc > 3 ? atoll(argv[3]) : 0;  // extra 100 KiB messages sharing the batch
-    const uint32_t cap = argc > 4 ? (uint32_t)atoi(argv[4]) : 148u;  // chain CTAs available to the planner
+    const uint32_t cap = argc > 4 ? (uint32_t)atoi(argv[4]) : 592u;  // chain CTAs available to the planner
     const uint64_t ssz = 100 * 1024;
     CK(configure_kernels());
     const uint64_t N = n + nsmall;
@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
                 CK(cudaMemcpyAsync(hq, qctl, 16, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 cudaEventRecord(e0, st);
-                if (mode) launch_chain_hash(d_base, d_off, d_len, chain_list, qctl, flags, sha[mode], md5[mode], states, false, cap, st2);
+                if (mode && hq[3] > 0) launch_chain_hash(d_base, d_off, d_len, chain_list, qctl, flags, sha[mode], md5[mode], states, false, (uint32_t)hq[3], st2);
                 launch_lane_hash(d_base, d_off, d_len, ring, qctl, N, flags, sha[mode], md5[mode], states, st);
                 CK(cudaStreamSynchronize(st2));
                 cudaEventRecord(e1, st);
