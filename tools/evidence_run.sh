@@ -1,4 +1,6 @@
 #!/bin/bash
+# Round-end evidence run: GPU test suite, bench line, ncu launch list, ncu --set full of the chain kernel, smoke, files bench.
+# Outputs land in gpurun_out/; the summaries kept under profiles/ are made from them with tools/launch_list_md.py and tools/ncu_summary.py.
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests_s2_final.txt 2>&1; tail -2 gpurun_out/gpu_tests_s2_final.txt
 python bench.py > gpurun_out/bench_s2.json 2> gpurun_out/bench_s2.err
