@@ -273,7 +273,8 @@ class Context:
     # -- files: stat + read + hash entirely inside the library (native reader threads, no mmap / Python I/O)
     @staticmethod
     def _c_paths(paths):
-        enc = [os.fsencode(p) for p in paths]
+        # callers that make several calls over one tree pass the paths already encoded (bytes) to pay fsencode once
+        enc = paths if (len(paths) and type(paths[0]) is bytes) else [os.fsencode(p) for p in paths]
         return enc, (ctypes.c_char_p * len(enc))(*enc)
 
     def stat_files(self, paths) -> tuple[np.ndarray, np.ndarray]:

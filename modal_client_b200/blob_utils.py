@@ -23,6 +23,7 @@ from __future__ import annotations
 import asyncio
 import dataclasses
 import functools
+import gc
 import mmap
 import os
 import platform
@@ -457,7 +458,7 @@ async def blob_iter(blob_id: str, stub):
 # ------------------------------------------------------------------------------- FileUploadSpec (v1)
 
 
-@dataclasses.dataclass
+@dataclasses.dataclass(slots=True)
 class FileUploadSpec:
     source: Callable[[], AbstractContextManager | BinaryIO]
     source_description: Any
@@ -534,7 +535,7 @@ def get_file_upload_spec_from_fileobj(fp: BinaryIO, mount_filename: PurePosixPat
 
 
 def get_file_upload_specs(
-    files: Sequence[tuple[Path, PurePosixPath, int | None]],
+    files: Sequence[tuple[Path | str, PurePosixPath | str, int | None]],
     cache_small_content: bool | None = None,
 ) -> list[FileUploadSpec]:
     """Batched ``get_file_upload_spec_from_path``: every file of a ``Volume.batch_upload`` / ``Mount`` goes
@@ -550,7 +551,7 @@ def get_file_upload_specs(
         return []
     ctx = get_context()
     n = len(files)
-    paths = [str(f[0]) for f in files]
+    paths = [os.fsencode(f[0]) for f in files]  # encoded once for the stat and the hash calls
     sizes, modes = ctx.stat_files(paths)
     # size classes, vectorised (same comparisons as _size_class)
     use_blob = sizes >= LARGE_FILE_LIMIT
@@ -573,28 +574,46 @@ def get_file_upload_specs(
         cache_small_content = n <= 4096
     sizes_l, modes_l = sizes.tolist(), modes.tolist()
     use_blob_l, want_md5_l, cache_l = use_blob.tolist(), want_md5.tolist(), cacheable.tolist()
+    # The per-file Python work below is what is left of a million-file tree once hashing takes a fraction of a second,
+    # so it is kept to positional construction and precomputed columns (~2.5 us per file).
+    partial, spec_cls, placeholder = functools.partial, FileUploadSpec, _MD5_PLACEHOLDER
     specs = []
+    append = specs.append
+    # a million small objects allocated in one go: without this the cyclic GC rescans the growing list again and again
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        _build_specs(files, append, spec_cls, partial, placeholder, cache_small_content, cache_l, use_blob_l, want_md5_l,
+                     sha_hex, md5_hex, modes_l, sizes_l)
+    finally:
+        if gc_was_on:
+            gc.enable()
+    return specs
+
+
+def _build_specs(files, append, spec_cls, partial, placeholder, cache_small_content, cache_l, use_blob_l, want_md5_l,
+                 sha_hex, md5_hex, modes_l, sizes_l) -> None:
     for i, (filename, mount_filename, mode) in enumerate(files):
         content = None
         if cache_small_content and cache_l[i]:
             with open(filename, "rb") as f:
                 content = f.read()
-        specs.append(
-            FileUploadSpec(
-                source=functools.partial(open, filename, "rb"),
-                source_description=filename,
-                source_is_path=isinstance(filename, Path),
-                mount_filename=mount_filename.as_posix() if isinstance(mount_filename, PurePosixPath)
+        append(
+            spec_cls(
+                partial(open, filename, "rb"),                                        # source
+                filename if isinstance(filename, Path) else Path(filename),           # source_description
+                True,                                                                 # source_is_path
+                mount_filename if type(mount_filename) is str                         # posix string from a trusted walk
+                else str(mount_filename) if type(mount_filename) is PurePosixPath
                 else PurePosixPath(mount_filename).as_posix(),
-                use_blob=use_blob_l[i],
-                sha256_hex=sha_hex[64 * i : 64 * i + 64],
-                md5_hex=md5_hex[32 * i : 32 * i + 32] if want_md5_l[i] else _MD5_PLACEHOLDER,
-                mode=(mode if mode else modes_l[i]) & 0o7777,
-                size=sizes_l[i],
-                content=content,
+                use_blob_l[i],
+                sha_hex[64 * i : 64 * i + 64],
+                md5_hex[32 * i : 32 * i + 32] if want_md5_l[i] else placeholder,
+                (mode if mode else modes_l[i]) & 0o7777,
+                sizes_l[i],
+                content,
             )
         )
-    return specs
 
 
 def first_occurrence_of_specs(specs: Sequence[FileUploadSpec]) -> tuple[list[int], int]:
@@ -750,27 +769,36 @@ async def file_upload_specs2(
 
     def run() -> list[FileUploadSpec2]:
         ctx = get_context()
-        paths = [str(f[0]) for f in files]
+        paths = [os.fsencode(f[0]) for f in files]  # encoded once for the stat and the hash calls
         sizes, modes = ctx.stat_files(paths)
         sha, _, trimmed = ctx.hash_files(paths, sizes, BLOCK_SIZE, _lib.SHA256 | _lib.TRIM_ZEROS)
         out, row = [], 0
         sizes_l, modes_l, trimmed_l, sha_raw = sizes.tolist(), modes.tolist(), trimmed.tolist(), sha.tobytes()
-        for i, (filename, mount_filename, mode) in enumerate(files):
-            size = sizes_l[i]
-            blocks = []
-            for start in range(0, size, BLOCK_SIZE):
-                blocks.append(FileUploadBlock(start, start + trimmed_l[row], sha_raw[32 * row : 32 * row + 32]))
-                row += 1
-            out.append(
-                FileUploadSpec2(
-                    source=functools.partial(open, filename, "rb"),
-                    source_description=filename,
-                    path=PurePosixPath(mount_filename).as_posix(),
-                    blocks=blocks,
-                    mode=(mode if mode else modes_l[i]) & 0o7777,
-                    size=size,
+        block_cls, spec_cls, partial, bs = FileUploadBlock, FileUploadSpec2, functools.partial, BLOCK_SIZE
+        gc_was_on = gc.isenabled()
+        gc.disable()  # bulk allocation of small objects: keep the cyclic GC from rescanning the growing lists
+        try:
+            for i, (filename, mount_filename, mode) in enumerate(files):
+                size = sizes_l[i]
+                blocks = []
+                for start in range(0, size, bs):
+                    blocks.append(block_cls(start, start + trimmed_l[row], sha_raw[32 * row : 32 * row + 32]))
+                    row += 1
+                out.append(
+                    spec_cls(
+                        source=partial(open, filename, "rb"),
+                        source_description=filename if isinstance(filename, Path) else Path(filename),
+                        path=mount_filename if type(mount_filename) is str
+                        else str(mount_filename) if type(mount_filename) is PurePosixPath
+                        else PurePosixPath(mount_filename).as_posix(),
+                        blocks=blocks,
+                        mode=(mode if mode else modes_l[i]) & 0o7777,
+                        size=size,
+                    )
                 )
-            )
+        finally:
+            if gc_was_on:
+                gc.enable()
         return out
 
     return await asyncio.to_thread(run)

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import asyncio
 import functools
+import os
 import time
 from collections.abc import Callable
 from io import BytesIO
@@ -39,7 +40,7 @@ class _BatchBase:
         self._client = client
         self._progress_cb = progress_cb or (lambda *_, **__: None)
         self._force = force
-        self._paths: list[tuple[Path, PurePosixPath, int | None]] = []
+        self._paths: list[tuple[Path | str, str, int | None]] = []  # (local path, remote posix path, mode)
         self._fileobjs: list[tuple[BinaryIO, PurePosixPath, int]] = []
 
     async def __aenter__(self):
@@ -51,18 +52,46 @@ class _BatchBase:
         if remote.endswith("/"):
             raise ValueError(f"remote_path ({remote}) must refer to a file - cannot end with /")
         if isinstance(local_file, (str, Path)):
-            self._paths.append((Path(local_file), PurePosixPath(remote), mode))
+            self._paths.append((local_file, remote, mode))
         else:
             self._fileobjs.append((local_file, PurePosixPath(remote), mode or 0o644))
 
     def put_directory(self, local_path: Path | str, remote_path: PurePosixPath | str, recursive: bool = True):
-        """Queue every regular file below ``local_path`` (directories and special files are skipped)."""
+        """Queue every regular file below ``local_path`` (directories and special files are skipped).
+
+        Same selection as the reference's ``rglob("*")`` + ``is_file()`` (py/modal/volume.py:1279-1284): symlinks to
+        files count, symlinked directories are not descended into, fifos / devices are skipped.  The walk itself is
+        ``os.scandir`` on plain strings: with hashing down to a fraction of a second, ``pathlib``'s ~15 us per file
+        (glob + ``is_file`` + ``relative_to`` + ``/``) would be most of a million-file upload."""
         local_path = Path(local_path)
         assert local_path.is_dir()
-        remote_path = PurePosixPath(remote_path)
-        for sub in (local_path.rglob("*") if recursive else local_path.glob("*")):
-            if sub.is_file():
-                self._paths.append((sub, remote_path / sub.relative_to(local_path), None))
+        remote_root = PurePosixPath(remote_path).as_posix().rstrip("/")
+        append = self._paths.append
+        for abs_path, rel_posix in _walk_files(os.fspath(local_path), recursive):
+            append((abs_path, f"{remote_root}/{rel_posix}", None))
+
+
+def _walk_files(root: str, recursive: bool):
+    """Yield (absolute path, path relative to ``root`` in posix form) of every regular file (or symlink to one)."""
+    stack = [(root, "")]
+    sep_is_posix = os.sep == "/"
+    while stack:
+        d, rel = stack.pop()
+        try:
+            it = os.scandir(d)
+        except OSError:
+            continue  # vanished or unreadable directory: pathlib's glob skips those too
+        with it:
+            for e in it:
+                name = e.name
+                try:
+                    if e.is_dir(follow_symlinks=False):
+                        if recursive:
+                            stack.append((e.path, f"{rel}{name}/"))
+                    elif e.is_file():  # follows symlinks, like Path.is_file()
+                        yield e.path, (f"{rel}{name}" if sep_is_posix else f"{rel}{name}".replace(os.sep, "/"))
+                except OSError:
+                    continue
 
 
 class VolumeUploadContextManager(_BatchBase):

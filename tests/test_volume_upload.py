@@ -166,3 +166,39 @@ def test_batch_upload_v2_missing_block_loop(backend, monkeypatch, tmp_path):
                 await blob_utils.ClientSessionRegistry.close_session()
 
     asyncio.run(run())
+
+
+def test_put_directory_walk_selects_what_rglob_is_file_selects(tmp_path):
+    """put_directory's scandir walk == the reference's `rglob("*")` + `is_file()` + `relative_to` (volume.py:1279-1284):
+    symlinks to files count, symlinked directories are not descended into, special files and directories are skipped."""
+    import os
+    from pathlib import Path, PurePosixPath
+
+    root = tmp_path / "src"
+    (root / "a" / "b").mkdir(parents=True)
+    (root / "empty_dir").mkdir()
+    for rel in ["top.txt", "a/x.bin", "a/b/deep.bin", "a/b/.hidden", "a/sp ace.txt"]:
+        (root / rel).write_bytes(rel.encode())
+    outside = tmp_path / "outside"
+    outside.mkdir()
+    (outside / "o.txt").write_bytes(b"o")
+    os.symlink(outside / "o.txt", root / "link_to_file")
+    os.symlink(outside, root / "link_to_dir")          # not descended into (rglob does not follow it either)
+    os.symlink(root / "nope", root / "dangling")       # is_file() false
+    os.mkfifo(root / "a" / "fifo")
+
+    def reference_way(recursive):
+        out = []
+        for sub in (root.rglob("*") if recursive else root.glob("*")):
+            if sub.is_file():
+                out.append((str(sub), (PurePosixPath("/dst") / sub.relative_to(root)).as_posix()))
+        return sorted(out)
+
+    for recursive in (True, False):
+        batch = volume._BatchBase("vo", client=None)
+        batch.put_directory(root, "/dst", recursive=recursive)
+        got = sorted((str(p), r) for p, r, _ in batch._paths)
+        assert got == reference_way(recursive)
+    batch = volume._BatchBase("vo", client=None)
+    batch.put_directory(str(root), PurePosixPath("/dst/"), recursive=True)  # str source, trailing slash on the remote
+    assert sorted(r for _, r, _ in batch._paths) == sorted(r for _, r in reference_way(True))
