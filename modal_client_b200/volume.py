@@ -20,6 +20,8 @@ from io import BytesIO
 from pathlib import Path, PurePosixPath
 from typing import Any, BinaryIO
 
+import numpy as np
+
 from . import _wire, blob_utils
 from ._logging import logger
 from .async_utils import gather_cancel_on_error, retry
@@ -249,5 +251,14 @@ async def _put_missing_blocks(file_specs, missing_blocks, put_responses: dict[by
             report(complete=True)
         return block.contents_sha256, data
 
-    for digest, resp in await gather_cancel_on_error(*(put_one(mb) for mb in missing_blocks)):
+    # Identical blocks (the same content in several files, repeated runs inside one file) are sent once per round: the
+    # put_response is kept per digest anyway (py/modal/volume.py:1464,1569).  First occurrences come from the GPU
+    # dedupe over the digests of the missing blocks; the reference uploads every listed block.
+    missing = list(missing_blocks)
+    if len(missing) > 1:
+        keys = np.frombuffer(b"".join(file_specs[mb.file_index].blocks[mb.block_index].contents_sha256 for mb in missing),
+                             np.uint8).reshape(len(missing), 32)
+        first, _ = await asyncio.to_thread(blob_utils.get_context().dedupe, keys)
+        missing = [mb for i, mb in enumerate(missing) if first[i] == i]
+    for digest, resp in await gather_cancel_on_error(*(put_one(mb) for mb in missing)):
         put_responses[digest] = resp

@@ -75,6 +75,7 @@ def _add_block_route(app_store, stub_holder, block_size):
             return web.Response(status=413, text="block too big")
         bid = hashlib.sha256(body).hexdigest()
         stub_holder["stub"].blocks[bid] = body
+        stub_holder["stub"].block_puts = getattr(stub_holder["stub"], "block_puts", 0) + 1
         return web.Response(text=f"test-put-response:{bid}")
 
     return put_block
@@ -158,6 +159,19 @@ def test_batch_upload_v2_missing_block_loop(backend, monkeypatch, tmp_path):
                 assert stub.volume_files["/v/blank"][0] == blank and stub.volume_files["/v/blank"][1] == 0o600
                 # trimmed blocks travelled trimmed: the blank blocks were sent as one byte
                 assert stub.blocks[hashlib.sha256(b"a").hexdigest()] == b"a"
+                # identical blocks (blank's two "a" blocks, ...) were PUT once each: one request per distinct content
+                assert stub.block_puts == len(stub.blocks)
+                # a second tree made of copies: every block is already known to the server after one round of PUTs
+                copies = tmp_path / "copies"
+                copies.mkdir()
+                payload = synth_bytes(999, 2 * BS + 17)
+                for k in range(5):
+                    (copies / f"same{k}.bin").write_bytes(payload)
+                before = stub.block_puts
+                async with volume.VolumeUploadContextManager2("vo-2", client) as batch:
+                    batch.put_directory(copies, "/copies")
+                assert stub.block_puts - before == 3  # 3 distinct blocks, not 15
+                assert all(stub.volume_files[f"/copies/same{k}.bin"][0] == payload for k in range(5))
                 with pytest.raises(FileExistsError):
                     async with volume.VolumeUploadContextManager2("vo-2", client) as batch:
                         batch.put_file(io.BytesIO(b"x"), "/v/blank")
