@@ -116,3 +116,22 @@ except Exception:
             self.volume_id = volume_id
             self.files = files or []
             self.disallow_overwrite_existing_files = disallow_overwrite_existing_files
+
+
+try:  # pragma: no cover
+    from modal_proto.api_pb2 import SharedVolumeGetFileRequest, SharedVolumePutFileRequest  # type: ignore
+except Exception:
+
+    @dataclasses.dataclass
+    class SharedVolumePutFileRequest:  # type: ignore[no-redef]  (api.proto:3555-3564)
+        shared_volume_id: str = ""
+        path: str = ""
+        sha256_hex: str = ""
+        data: bytes = b""
+        data_blob_id: str = ""
+        resumable: bool = False
+
+    @dataclasses.dataclass
+    class SharedVolumeGetFileRequest:  # type: ignore[no-redef]
+        shared_volume_id: str = ""
+        path: str = ""

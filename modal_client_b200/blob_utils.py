@@ -364,6 +364,10 @@ def _is_real_md5(h: UploadHashes) -> bool:
     return bool(h.md5_base64) and h.md5_hex() != _MD5_PLACEHOLDER
 
 
+def _is_real_md5_hex(md5_hex: str | None) -> bool:
+    return bool(md5_hex) and md5_hex != _MD5_PLACEHOLDER
+
+
 async def blob_upload_with_r2_failure_info(payload: bytes, stub) -> tuple[str, bool, int]:
     if isinstance(payload, str):
         logger.debug("Blob uploading string, not bytes - auto-encoding as utf8")
