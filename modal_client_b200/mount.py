@@ -129,7 +129,12 @@ def _select_files(entries: Sequence[_MountEntry]) -> list[tuple[Path, PurePosixP
 def get_file_specs(entries: Sequence[_MountEntry]) -> list[FileUploadSpec]:
     """``_Mount._get_files`` (mount.py:465-485) as one batch.  A file that disappears between selection and
     reading (editors' temp files) is ignored with a log line, like the reference's ``except FileNotFoundError``."""
-    selected = [(p, r) for p, r in _select_files(entries) if p.is_file() or _log_vanished(p)]
+    selected = []
+    for p, r in _select_files(entries):
+        if p.is_file():
+            selected.append((p, r))
+        else:  # removed between selection and now (editors' temp files): the reference's `except FileNotFoundError`
+            logger.info(f"Ignoring file not found: {p}")
     logger.debug(f"Computing checksums for {len(selected)} files on the GPU")
     try:
         return blob_utils.get_file_upload_specs([(p, r, None) for p, r in selected])
@@ -144,11 +149,6 @@ def get_file_specs(entries: Sequence[_MountEntry]) -> list[FileUploadSpec]:
             except FileNotFoundError as exc2:
                 logger.info(f"Ignoring file not found: {exc2}")
         return specs
-
-
-def _log_vanished(p: Path) -> bool:
-    logger.info(f"Ignoring file not found: {p}")
-    return False
 
 
 def _description(entries: Sequence[_MountEntry]) -> str:

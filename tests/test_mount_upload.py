@@ -188,3 +188,33 @@ def test_first_occurrence_of_specs_follows_the_set_walk(backend, tmp_path):
     want, want_nd = ref_port.first_occurrence([bytes.fromhex(s.sha256_hex) for s in specs])
     assert first == want and nd == want_nd == len({hashlib.sha256(d).digest() for d in files.values()})
     assert blob_utils.first_occurrence_of_specs([]) == ([], 0)
+
+
+def test_mount_dir_symlinked_file_keeps_its_name(backend, tmp_path):
+    """py/test/mount_test.py `test_mount_directory_with_symlinked_file`: a symlink inside the mounted directory is
+    uploaded under the LINK's name with the TARGET's content (local paths are resolved per file, not for the directory)."""
+    target_dir = tmp_path / "elsewhere"
+    target_dir.mkdir()
+    (target_dir / "real.txt").write_bytes(b"real content")
+    root = tmp_path / "mounted"
+    root.mkdir()
+    os.symlink(target_dir / "real.txt", root / "alias.txt")
+    sel = mount._select_files([mount._MountDir(root, PurePosixPath("/m"))])
+    assert [(p, r.as_posix()) for p, r in sel] == [((target_dir / "real.txt").resolve(), "/m/alias.txt")]
+    specs = mount.get_file_specs([mount._MountDir(root, PurePosixPath("/m"))])
+    assert [(s.mount_filename, s.sha256_hex) for s in specs] == [("/m/alias.txt", hashlib.sha256(b"real content").hexdigest())]
+    # a file that disappears after selection is skipped, not fatal
+    ghost = root / "ghost.tmp"
+    ghost.write_bytes(b"x")
+    entries = [mount._MountDir(root, PurePosixPath("/m"))]
+    real_select = mount._select_files
+
+    def select_then_delete(e):
+        out = real_select(e)
+        ghost.unlink(missing_ok=True)
+        return out
+
+    import unittest.mock as um
+    with um.patch.object(mount, "_select_files", select_then_delete):
+        specs = mount.get_file_specs(entries)
+    assert [s.mount_filename for s in specs] == ["/m/alias.txt"]
