@@ -117,7 +117,10 @@ __device__ __forceinline__ uint32_t addv(uint32_t a, uint32_t b) {
 }
 #define ADD(x, y) addv((x), (y))
 #else
-#define ADD(x, y) addf((x), (y), one)
+// kPlainAdd (a constant where ADD is expanded): false = the add is issued as IMAD on the FMA pipe (dense batches:
+// the ALU pipe is the bottleneck); true = plain add, ptxas fuses pairs into IADD3 / LEA (sparse batches: a warp
+// alone on its SMSP issues one instruction per two cycles whatever the pipe, so fewer instructions win).
+#define ADD(x, y) (kPlainAdd ? ((x) + (y)) : addf((x), (y), one))
 #endif
 // B200H_SHAONLY_ROT: in the SHA-256-only instantiation the ALU pipe carries 1040 of the 1640 instructions
 // per block while the FMA pipe idles, so some shifts are moved over as multiplies:
@@ -253,12 +256,13 @@ __constant__ uint32_t kShaK[48] = {
 
 // The two hashes are independent dependency chains over the same 16 words, so their rounds are
 // interleaved at source level (4 SHA rounds : 4 MD5 steps) to give every warp two chains of ILP.
-template <bool DO_SHA, bool DO_MD5>
+template <bool DO_SHA, bool DO_MD5, bool SPARSE = false>
 __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], const uint32_t (&x)[16],
                                          bool is_last, uint32_t bits_lo, uint32_t bits_hi, uint32_t one) {
+    constexpr bool kPlainAdd = SPARSE;
     uint32_t w[16];
     uint32_t m14 = x[14], m15 = x[15];
-    constexpr int kShaRot = DO_MD5 ? 0 : (B200H_SHAONLY_ROT);
+    constexpr int kShaRot = (DO_MD5 || SPARSE) ? 0 : (B200H_SHAONLY_ROT);  // multiplies add instructions: dense only
     const uint32_t m29 = one << 29, m22 = one << 22;  // 2^29, 2^22 as run-time values (bit 2 of kShaRot)
     (void)m29; (void)m22;
     if (DO_SHA) {
@@ -441,7 +445,10 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 // are waiting* and pops the next ones, so n messages share S < n lanes evenly (no wave quantisation) and
 // mixed sizes balance like longest-first list scheduling.  Digest chaining state travels through st[].
 // (6 CTAs/SM was also tried for the MD5-only instantiation: 3.39 TB/s at full occupancy vs 3.42 at 5 -- no gain.)
-template <bool DO_SHA, bool DO_MD5>
+// SPARSE: instantiation for batches that leave every warp alone on its SMSP (<= 4 warps per SM): such a warp is
+// bound by its own issue rate (one instruction per two cycles), so the adds are left to ptxas (IADD3 / LEA fusion,
+// ~15 % fewer instructions per block) instead of being spread over the FMA pipe.
+template <bool DO_SHA, bool DO_MD5, bool SPARSE>
 __global__ void __launch_bounds__(kLaneThreads, B200H_LANE_MIN_CTAS)
 lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
                  uint32_t* __restrict__ ring, uint32_t ring_mask, int* __restrict__ qctl, uint32_t flags,
@@ -690,7 +697,7 @@ lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
                         for (int k = 0; k < 16; ++k) x[k] = 0u;
                     }
                     const bool is_last = ntail && (step + 1 == nsteps);
-                    compress<DO_SHA, DO_MD5>(hs, hm, x, is_last, bits_lo, bits_hi, one);
+                    compress<DO_SHA, DO_MD5, SPARSE>(hs, hm, x, is_last, bits_lo, bits_hi, one);
                 }
             }
             issue(c + kStages);  // refill the slot just consumed (an empty group when nothing is left)
@@ -908,6 +915,7 @@ chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
                   const uint32_t* __restrict__ chain_list, const int* __restrict__ qctl, uint32_t flags,
                   uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out, ChainState* __restrict__ st,
                   int resume, uint32_t one) {
+    constexpr bool kPlainAdd = false;  // ADD() inside CH_RND: the one off-path sum stays an IMAD
     const uint32_t n_chain = (uint32_t)qctl[3];
     if (blockIdx.x >= n_chain) return;  // entry e lives in CTA e % gridDim.x: this CTA has none
     extern __shared__ __align__(128) uint8_t smem_all[];
@@ -1393,11 +1401,11 @@ int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* 
     return 1;
 }
 
-template <bool S, bool M>
+template <bool S, bool M, bool SP>
 static void launch_lane_t(int grid, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring,
                           uint32_t ring_mask, int* qctl, uint32_t flags, int lpw, uint32_t quantum, uint8_t* sha_out,
                           uint8_t* md5_out, ChainState* state, cudaStream_t st) {
-    lane_hash_kernel<S, M><<<grid, kLaneThreads, kLaneSmem, st>>>(base, off, len, ring, ring_mask, qctl, flags, lpw,
+    lane_hash_kernel<S, M, SP><<<grid, kLaneThreads, kLaneSmem, st>>>(base, off, len, ring, ring_mask, qctl, flags, lpw,
                                                                 quantum, sha_out, md5_out, state, 1u);
 }
 
@@ -1428,9 +1436,19 @@ int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* l
         return (uint32_t)(v > 0 ? v : 32);
     }();
     const bool s = flags & F_SHA256, m = flags & F_MD5;
-    if (s && m) launch_lane_t<true, true>(grid, base, off, len, ring, mask, qctl, flags, lpw, quantum, sha_out, md5_out, state, st);
-    else if (s) launch_lane_t<true, false>(grid, base, off, len, ring, mask, qctl, flags, lpw, quantum, sha_out, md5_out, state, st);
-    else if (m) launch_lane_t<false, true>(grid, base, off, len, ring, mask, qctl, flags, lpw, quantum, sha_out, md5_out, state, st);
+    // every warp alone on its SMSP -> the minimum-instruction instantiation (SHA-256 kernels; MD5 alone is latency bound)
+    const bool sparse = warps <= min_warps && getenv("B200H_NO_SPARSE") == nullptr;
+#define LANE_ARGS grid, base, off, len, ring, mask, qctl, flags, lpw, quantum, sha_out, md5_out, state, st
+    if (s && m) {
+        if (sparse) launch_lane_t<true, true, true>(LANE_ARGS);
+        else launch_lane_t<true, true, false>(LANE_ARGS);
+    } else if (s) {
+        if (sparse) launch_lane_t<true, false, true>(LANE_ARGS);
+        else launch_lane_t<true, false, false>(LANE_ARGS);
+    } else if (m) {
+        launch_lane_t<false, true, false>(LANE_ARGS);
+    }
+#undef LANE_ARGS
     else return 0;
     return 1;
 }
@@ -1446,12 +1464,13 @@ int chain_groups_per_cta() { return kChainGroups; }
 
 cudaError_t configure_kernels() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(lane_hash_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lane_hash_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lane_hash_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
-    if (e != cudaSuccess) return e;
+    const void* lane_kernels[5] = {(const void*)lane_hash_kernel<true, true, false>, (const void*)lane_hash_kernel<true, false, false>,
+                                   (const void*)lane_hash_kernel<false, true, false>, (const void*)lane_hash_kernel<true, true, true>,
+                                   (const void*)lane_hash_kernel<true, false, true>};
+    for (const void* k : lane_kernels) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
+        if (e != cudaSuccess) return e;
+    }
     e = cudaFuncSetAttribute(chain_hash_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(chain_hash_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem);
@@ -1464,13 +1483,13 @@ cudaError_t configure_kernels() {
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     if (sms > 0) g_sm_count = sms;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, lane_hash_kernel<true, true>, kLaneThreads, kLaneSmem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, lane_hash_kernel<true, true, false>, kLaneThreads, kLaneSmem);
     if (e != cudaSuccess) return e;
     if (ctas > 0) g_lane_ctas_per_sm[0] = ctas;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, lane_hash_kernel<true, false>, kLaneThreads, kLaneSmem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, lane_hash_kernel<true, false, false>, kLaneThreads, kLaneSmem);
     if (e != cudaSuccess) return e;
     if (ctas > 0) g_lane_ctas_per_sm[1] = ctas;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, lane_hash_kernel<false, true>, kLaneThreads, kLaneSmem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, lane_hash_kernel<false, true, false>, kLaneThreads, kLaneSmem);
     if (e != cudaSuccess) return e;
     if (ctas > 0) g_lane_ctas_per_sm[2] = ctas;
     return cudaSuccess;

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(128) chain_bench(uint32_t* out, long long* cyc
     __shared__ __align__(16) uint32_t rows[32][68];  // 32 blocks of 64 W+K words (or 16 message words), padded
     for (int i = threadIdx.x; i < 32 * 68; i += blockDim.x) (&rows[0][0])[i] = seed * 2654435761u + i * 40503u;
     __syncthreads();
+    constexpr bool kPlainAdd = false;  // ADD() inside the CH_RND variants
     uint32_t hs[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
     uint32_t hm[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
     const long long t0 = clock64();
@@ -97,6 +98,8 @@ __global__ void __launch_bounds__(128) chain_bench(uint32_t* out, long long* cyc
             if (MODE == 1) compress<true, false>(hs, hm, x, false, 0u, 0u, one);
             if (MODE == 2) compress<false, true>(hs, hm, x, false, 0u, 0u, one);
             if (MODE == 3) compress<true, true>(hs, hm, x, false, 0u, 0u, one);
+            if (MODE == 10) compress<true, true, true>(hs, hm, x, false, 0u, 0u, one);
+            if (MODE == 11) compress<true, false, true>(hs, hm, x, false, 0u, 0u, one);
         }
     }
     const long long t1 = clock64();
@@ -137,6 +140,8 @@ int main() {
     run<7>("MD5 from M+T rows, IADD3 + LEA.HI", 1);
     run<8>("MD5 from M+T rows, IADD3 + SHF + IMAD", 1);
     run<9>("MD5 md5_chain_block (shipped)", 1);
+    run<10>("fused, sparse instantiation (plain adds)", 1);
+    run<11>("SHA-256 full, sparse instantiation", 1);
     for (int w : {1, 4}) {
         run<0>("rounds only, all adds IMAD", w);
         run<1>("SHA-256 full (schedule + rounds)", w);
