@@ -45,3 +45,32 @@ async def gather_cancel_on_error(*coros):
             t.cancel()
         await asyncio.gather(*tasks, return_exceptions=True)
         raise
+
+
+async def bounded_map(items, fn, concurrency: int) -> list:
+    """``[await fn(x) for x in items]`` with at most ``concurrency`` calls in flight, results in input order.
+
+    The reference drives its uploads with ``async_map(generator, fn, concurrency=N)`` (py/modal/_utils/async_utils.py),
+    which keeps N coroutines alive however long the input is; this is the same bound for an input that is already a
+    list -- a fixed set of worker tasks pulling indices -- instead of one task (plus a semaphore wait) per item,
+    which for a million-file tree is a million pending tasks.  The first failure cancels the rest and re-raises."""
+    items = list(items)
+    n = len(items)
+    results: list = [None] * n
+    if n == 0:
+        return results
+    indices = iter(range(n))
+
+    async def worker():
+        for i in indices:  # one shared iterator: the event loop is single-threaded, every index is taken once
+            results[i] = await fn(items[i])
+
+    workers = [asyncio.ensure_future(worker()) for _ in range(max(1, min(concurrency, n)))]
+    try:
+        await asyncio.gather(*workers)
+    except BaseException:
+        for w in workers:
+            w.cancel()
+        await asyncio.gather(*workers, return_exceptions=True)
+        raise
+    return results

@@ -41,7 +41,7 @@ from . import _lib, _wire, hash_utils
 from ._backend import get_context
 from ._logging import logger
 from ._wire import BlobCreateRequest
-from .async_utils import asyncnullcontext, gather_cancel_on_error, retry
+from .async_utils import asyncnullcontext, bounded_map, gather_cancel_on_error, retry
 from .exception import ExecutionError
 from .hash_utils import UploadHashes, get_upload_hashes
 from .http_utils import ClientSessionRegistry
@@ -391,13 +391,8 @@ async def blob_upload_many(payloads: Sequence[bytes], stub, concurrency: int | N
     the reference's concurrency (BLOB_MAX_PARALLELISM).  Order is preserved."""
     payloads = [p.encode("utf8") if isinstance(p, str) else p for p in payloads]
     hashes = await asyncio.to_thread(hash_utils.get_upload_hashes_many, payloads)
-    sem = asyncio.Semaphore(concurrency or BLOB_MAX_PARALLELISM)
-
-    async def one(h, p):
-        async with sem:
-            return await _blob_upload(h, p, stub)
-
-    return list(await gather_cancel_on_error(*(one(h, p) for h, p in zip(hashes, payloads))))
+    jobs = list(zip(hashes, payloads))
+    return await bounded_map(jobs, lambda hp: _blob_upload(hp[0], hp[1], stub), concurrency or BLOB_MAX_PARALLELISM)
 
 
 async def format_blob_data(data: bytes, api_stub) -> dict[str, Any]:

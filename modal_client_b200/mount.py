@@ -32,6 +32,7 @@ from pathlib import Path, PurePosixPath
 from . import _wire, blob_utils
 from ._lib import B200HashError
 from ._logging import logger
+from .async_utils import bounded_map
 from .blob_utils import FileUploadSpec
 from .exception import ExecutionError, MountUploadTimeoutError
 
@@ -181,7 +182,6 @@ async def load_mount(
     logger.debug(f"Creating mount {message_label}: {len(specs)} files, {n_distinct} distinct contents")
 
     blob_upload_concurrency = asyncio.Semaphore(16)  # limit uploads of large files (mount.py:503)
-    slots = asyncio.Semaphore(n_concurrent_uploads)  # async_map(..., concurrency=64) (mount.py:573-577)
     total_uploads, total_bytes = 0, 0
 
     async def _put_file(file_spec: FileUploadSpec) -> None:
@@ -217,19 +217,9 @@ async def load_mount(
                 return
         raise MountUploadTimeoutError(f"Mounting of {file_spec.source_description} timed out")
 
-    async def _guarded(spec):
-        async with slots:
-            await _put_file(spec)
-
-    # only the first occurrence of a content is checked / sent; the others just appear in the index
-    uploads = [asyncio.ensure_future(_guarded(s)) for i, s in enumerate(specs) if first[i] == i]
-    try:
-        await asyncio.gather(*uploads)
-    except BaseException:
-        for t in uploads:
-            t.cancel()
-        await asyncio.gather(*uploads, return_exceptions=True)
-        raise
+    # only the first occurrence of a content is checked / sent; the others just appear in the index.
+    # n_concurrent_uploads in flight, as async_map(..., concurrency=64) does in the reference (mount.py:573-577)
+    await bounded_map([s for i, s in enumerate(specs) if first[i] == i], _put_file, concurrency=n_concurrent_uploads)
 
     files = [_wire.MountFile(filename=s.mount_filename, sha256_hex=s.sha256_hex, mode=s.mode) for s in specs]
     if not files:

@@ -21,6 +21,7 @@ from pathlib import Path, PurePosixPath
 from typing import Any, BinaryIO
 
 from . import _wire, blob_utils
+from .async_utils import bounded_map
 from .blob_utils import LARGE_FILE_LIMIT, blob_iter, blob_upload_file
 from .hash_utils import get_sha256_hex
 from .volume import _walk_files
@@ -100,15 +101,13 @@ class NetworkFileSystemUploader:
         files = [(abs_path, f"{remote_root.rstrip('/')}/{rel}", None)
                  for abs_path, rel in _walk_files(os.fspath(_local_path), recursive=True)]
         specs = await asyncio.to_thread(blob_utils.get_file_upload_specs, files, False)
-        sem = asyncio.Semaphore(concurrency)
 
         async def one(spec) -> int:
-            async with sem:
-                with spec.source() as fp:
-                    md5_hex = spec.md5_hex if blob_utils._is_real_md5_hex(spec.md5_hex) else None
-                    return await self._write(spec.mount_filename, fp, spec.size, spec.sha256_hex, md5_hex, progress)
+            with spec.source() as fp:
+                md5_hex = spec.md5_hex if blob_utils._is_real_md5_hex(spec.md5_hex) else None
+                return await self._write(spec.mount_filename, fp, spec.size, spec.sha256_hex, md5_hex, progress)
 
-        return sum(await asyncio.gather(*(one(s) for s in specs)))
+        return sum(await bounded_map(specs, one, concurrency=concurrency))
 
 
 __all__ = ["NETWORK_FILE_SYSTEM_PUT_FILE_CLIENT_TIMEOUT", "LARGE_FILE_LIMIT", "NetworkFileSystemUploader"]

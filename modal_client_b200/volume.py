@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _wire, blob_utils
 from ._logging import logger
-from .async_utils import gather_cancel_on_error, retry
+from .async_utils import bounded_map, retry
 from .blob_utils import FileUploadSpec, FileUploadSpec2, _ByteBudget
 from .exception import ExecutionError
 from .http_utils import ClientSessionRegistry
@@ -110,31 +110,16 @@ class VolumeUploadContextManager(_BatchBase):
         for fp, remote, mode in self._fileobjs:
             specs.append(await asyncio.to_thread(blob_utils.get_file_upload_spec_from_fileobj, fp, remote, mode))
         logger.debug(f"Computed checksums for {len(specs)} files on the GPU")
-        sem = asyncio.Semaphore(20)  # upload concurrency of the reference (volume.py:1220)
         # In-batch dedupe on the digest table, computed on the GPU (b200h_dedupe_host; what Mount does with a set,
-        # py/modal/mount.py:498,518-534): each distinct content is checked / uploaded once, however many paths
-        # carry it; the other paths wait for that upload and only appear in the file index.
+        # py/modal/mount.py:498,518-534): each distinct content is checked / uploaded once, however many paths carry
+        # it; the other paths only appear in the file index.  20 uploads in flight, like the reference (volume.py:1220).
         first, _ = await asyncio.to_thread(blob_utils.first_occurrence_of_specs, specs)
-        loop = asyncio.get_running_loop()
-        done_of = {i: loop.create_future() for i in set(first)}
-
-        async def one(i, spec):
-            if first[i] != i:
-                await done_of[first[i]]
+        owners = [i for i, f in enumerate(first) if f == i]
+        await bounded_map(owners, lambda i: self._upload_file(specs[i]), concurrency=20)
+        for i, spec in enumerate(specs):
+            if first[i] != i:  # a copy of something already sent: account for it in the progress display
                 self._progress_cb(task_id=self._progress_cb(name=spec.mount_filename, size=spec.size), complete=True)
-                return _wire.MountFile(filename=spec.mount_filename, sha256_hex=spec.sha256_hex, mode=spec.mode)
-            fut = done_of[i]
-            try:
-                async with sem:
-                    out = await self._upload_file(spec)
-                fut.set_result(None)
-                return out
-            except BaseException as exc:
-                fut.set_exception(exc)
-                fut.exception()  # mark retrieved; waiters re-raise it
-                raise
-
-        files = list(await gather_cancel_on_error(*(one(i, s) for i, s in enumerate(specs))))
+        files = [_wire.MountFile(filename=s.mount_filename, sha256_hex=s.sha256_hex, mode=s.mode) for s in specs]
         self._progress_cb(complete=True)
         request = _wire.VolumePutFilesRequest(volume_id=self._volume_id, files=files,
                                               disallow_overwrite_existing_files=not self._force)
@@ -220,7 +205,6 @@ async def _put_missing_blocks(file_specs, missing_blocks, put_responses: dict[by
     server's put_response per block digest (py/modal/volume.py:1500-1574)."""
     from .bytes_io_segment_payload import BytesIOSegmentPayload
 
-    sem = asyncio.Semaphore(put_concurrency)
     pending: dict[str, tuple[Any, set[int]]] = {}
 
     async def put_one(mb) -> tuple[bytes, bytes]:
@@ -240,12 +224,11 @@ async def _put_missing_blocks(file_specs, missing_blocks, put_responses: dict[by
                         raise ExecutionError(f"block PUT failed with status {resp.status}: {await resp.text()}")
                     return await resp.content.read()
 
-        async with sem:
-            with spec.source() as fp:
-                # the block digest is already known (GPU batch): no re-hash while sending
-                payload = BytesIOSegmentPayload(fp, block.start, block.end - block.start, chunk_size=256 * 1024,
-                                                progress_report_cb=report, md5_digest=b"\0" * 16)
-                data = await attempt(payload)
+        with spec.source() as fp:
+            # the block digest is already known (GPU batch): no re-hash while sending
+            payload = BytesIOSegmentPayload(fp, block.start, block.end - block.start, chunk_size=256 * 1024,
+                                            progress_report_cb=report, md5_digest=b"\0" * 16)
+            data = await attempt(payload)
         waiting.discard(mb.block_index)
         if not waiting:
             report(complete=True)
@@ -260,5 +243,5 @@ async def _put_missing_blocks(file_specs, missing_blocks, put_responses: dict[by
                              np.uint8).reshape(len(missing), 32)
         first, _ = await asyncio.to_thread(blob_utils.get_context().dedupe, keys)
         missing = [mb for i, mb in enumerate(missing) if first[i] == i]
-    for digest, resp in await gather_cancel_on_error(*(put_one(mb) for mb in missing)):
+    for digest, resp in await bounded_map(missing, put_one, concurrency=put_concurrency):
         put_responses[digest] = resp

@@ -313,3 +313,42 @@ def test_use_md5_hosts():
     assert not blob_utils.use_md5("http://localhost:9000/x") and not blob_utils.use_md5("http://127.0.0.1:1/x")
     with pytest.raises(Exception, match="Unknown S3 host"):
         blob_utils.use_md5("https://example.com/x")
+
+
+def test_bounded_map_order_bound_and_failure():
+    """async_utils.bounded_map: results in input order, never more than `concurrency` calls in flight, a fixed number
+    of tasks whatever the input length, first failure cancels the rest."""
+    from modal_client_b200.async_utils import bounded_map
+
+    async def run():
+        live, peak, started = 0, 0, []
+
+        async def fn(x):
+            nonlocal live, peak
+            live += 1
+            peak = max(peak, live)
+            started.append(x)
+            await asyncio.sleep(0.001 * (x % 3))
+            live -= 1
+            return x * x
+
+        before = len(asyncio.all_tasks())
+        out = await bounded_map(range(200), fn, concurrency=7)
+        assert out == [x * x for x in range(200)] and peak == 7 and len(asyncio.all_tasks()) == before
+        assert await bounded_map([], fn, concurrency=3) == []
+        assert await bounded_map([5], fn, concurrency=100) == [25]
+
+        async def boom(x):
+            await asyncio.sleep(0.001)
+            if x == 13:
+                raise ValueError("thirteen")
+            await asyncio.sleep(0.05)
+            return x
+
+        started.clear()
+        with pytest.raises(ValueError, match="thirteen"):
+            await bounded_map(range(1000), boom, concurrency=4)
+        await asyncio.sleep(0.1)
+        assert len(asyncio.all_tasks()) == before  # the workers were cancelled, nothing keeps running
+
+    asyncio.run(run())
