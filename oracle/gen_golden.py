@@ -239,11 +239,114 @@ def gen_multipart(b, seg):
     return {"source": "py/modal/_utils/blob_utils.py:159-234 + bytes_io_segment_payload.py (unmodified)", "cases": out}
 
 
+# ---------------------------------------------------------------------------------- mount file selection
+
+MOUNT_TREE = {  # relative path -> ("file", seed, size) | ("link", target relative to the tmp dir) ; dirs are implied
+    "pkg/a.py": ("file", 1, 15),
+    "pkg/sub/b.py": ("file", 2, 400),
+    "pkg/sub/c.bin": ("file", 3, 70_000),
+    "pkg/sub/__pycache__/b.pyc": ("file", 4, 30),
+    "pkg/.git/config": ("file", 5, 20),
+    "pkg/.hidden": ("file", 6, 5),
+    "pkg/empty": ("file", 7, 0),
+    "pkg/sp ace/x y.txt": ("file", 8, 9),
+    "pkg/alias.txt": ("link", "outside/real.txt"),
+    "pkg/linked_dir": ("link", "outside"),
+    "pkg/dangling": ("link", "outside/nope"),
+    "outside/real.txt": ("file", 9, 12),
+}
+
+
+def build_mount_tree(root):
+    """Materialise MOUNT_TREE below ``root`` (used by this generator and by tests/test_mount_upload.py)."""
+    from modal_client_b200.synth import synth_bytes
+
+    for rel, spec in MOUNT_TREE.items():
+        p = os.path.join(root, rel)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        if spec[0] == "file":
+            with open(p, "wb") as f:
+                f.write(synth_bytes(spec[1], spec[2]))
+    for rel, spec in MOUNT_TREE.items():
+        if spec[0] == "link":
+            os.symlink(os.path.join(root, spec[1]), os.path.join(root, rel))
+
+
+def mount_ignore(rel) -> bool:
+    """The ignore predicate of the golden cases (plain callable: no directory pruning in the reference)."""
+    return rel.suffix == ".pyc" or any(part.startswith(".") for part in rel.parts)
+
+
+def reference_mount_entries():
+    """The reference's OWN ``_MountEntry`` / ``_MountFile`` / ``_MountDir`` / ``_select_files`` (py/modal/mount.py:89-196),
+    compiled from the unmodified source file: only these four definitions are executed, in a namespace holding the
+    standard-library names they use and a stand-in for ``modal.file_pattern_matcher._AbstractPatternMatcher``."""
+    import abc
+    import ast
+    import dataclasses
+    import types
+    import typing
+    from collections.abc import Callable, Generator
+    from pathlib import Path
+
+    path = os.path.join(os.path.dirname(ref_shim.package_dir()), "modal", "mount.py")
+    tree = ast.parse(open(path).read())
+    wanted = {"_MountEntry", "_select_files", "_MountFile", "_MountDir"}
+    body = [n for n in tree.body if getattr(n, "name", None) in wanted]
+    assert {n.name for n in body} == wanted
+
+    class _AbstractPatternMatcher:  # nothing in the golden cases is one
+        pass
+
+    fake_modal = types.SimpleNamespace(file_pattern_matcher=types.SimpleNamespace(_AbstractPatternMatcher=_AbstractPatternMatcher))
+    ns = {"abc": abc, "dataclasses": dataclasses, "os": os, "typing": typing, "Path": Path, "PurePosixPath": PurePosixPath,
+          "Callable": Callable, "Generator": Generator, "modal": fake_modal}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def mount_cases(entries_ns, root):
+    """name -> list of entries, built from the classes in ``entries_ns`` (the reference's or ours)."""
+    from pathlib import Path
+
+    D, F = entries_ns["_MountDir"], entries_ns["_MountFile"]
+    pkg = Path(root) / "pkg"
+    nothing = lambda _p: False  # noqa: E731
+    return {
+        "dir_recursive": [D(pkg, PurePosixPath("/root/pkg"), nothing, True)],
+        "dir_recursive_ignore": [D(pkg, PurePosixPath("/root/pkg"), mount_ignore, True)],
+        "dir_flat": [D(pkg, PurePosixPath("/x"), nothing, False)],
+        "file_and_overlap": [F(pkg / "a.py", PurePosixPath("/root/a.py")), D(pkg / "sub", PurePosixPath("/s"), nothing, True),
+                             D(pkg / "sub", PurePosixPath("/s"), nothing, True)],
+        "file_via_symlink": [F(pkg / "alias.txt", PurePosixPath("/root/alias.txt"))],
+    }
+
+
+def normalise_selection(pairs, root):
+    """[(local Path, remote PurePosixPath)] -> sorted [[local relative to the resolved root, remote posix]]."""
+    from pathlib import Path
+
+    base = Path(root).resolve()
+    return sorted([os.path.relpath(str(p), str(base)), r.as_posix()] for p, r in pairs)
+
+
+def gen_mount_select():
+    import tempfile
+
+    ns = reference_mount_entries()
+    with tempfile.TemporaryDirectory() as tmp:
+        build_mount_tree(tmp)
+        cases = {name: normalise_selection(ns["_select_files"](entries), tmp) for name, entries in mount_cases(ns, tmp).items()}
+    return {"source": "py/modal/mount.py:89-196 (_MountFile, _MountDir, _select_files; unmodified source, executed)",
+            "tree": {k: list(v) for k, v in MOUNT_TREE.items()}, "cases": cases}
+
+
 def main():
     h, b, seg = ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
     for name, doc in [("hash_utils.json", gen_hash_utils(h)), ("file_specs.json", gen_file_specs(b)),
-                      ("blocks.json", gen_blocks(b)), ("multipart.json", gen_multipart(b, seg))]:
+                      ("blocks.json", gen_blocks(b)), ("multipart.json", gen_multipart(b, seg)),
+                      ("mount_select.json", gen_mount_select())]:
         with open(os.path.join(OUT, name), "w") as f:
             json.dump(doc, f, indent=1, sort_keys=True)
             f.write("\n")

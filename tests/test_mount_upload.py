@@ -218,3 +218,37 @@ def test_mount_dir_symlinked_file_keeps_its_name(backend, tmp_path):
     with um.patch.object(mount, "_select_files", select_then_delete):
         specs = mount.get_file_specs(entries)
     assert [s.mount_filename for s in specs] == ["/m/alias.txt"]
+
+
+def _selection_cases(tmp_path):
+    from oracle import gen_golden
+
+    gen_golden.build_mount_tree(str(tmp_path))
+    ours = {"_MountDir": mount._MountDir, "_MountFile": mount._MountFile}
+    return gen_golden, {name: gen_golden.normalise_selection(mount._select_files(entries), str(tmp_path))
+                        for name, entries in gen_golden.mount_cases(ours, str(tmp_path)).items()}
+
+
+def test_mount_selection_matches_reference_golden(tmp_path):
+    """_MountFile / _MountDir / _select_files select exactly what the reference's own classes select on the fixture
+    tree of oracle/gen_golden.py (tests/golden/mount_select.json was produced by executing py/modal/mount.py:89-196
+    unmodified): symlinked files under the link's name, symlinked directories not descended into, dangling links
+    listed by the recursive walk but not by the flat one, ignore predicate applied to relative paths, overlaps merged."""
+    import json
+
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mount_select.json")))
+    _, got = _selection_cases(tmp_path)
+    assert got == golden["cases"]
+    assert len(golden["cases"]["dir_recursive"]) == 10 and len(golden["cases"]["dir_flat"]) == 4
+
+
+def test_mount_selection_matches_live_reference(tmp_path):
+    from oracle import ref_shim
+
+    if not ref_shim.available() or not os.path.isfile(os.path.join(os.path.dirname(ref_shim.package_dir()), "modal", "mount.py")):
+        pytest.skip("no copy of the reference here")
+    gen_golden, got = _selection_cases(tmp_path)
+    ns = gen_golden.reference_mount_entries()
+    want = {name: gen_golden.normalise_selection(ns["_select_files"](entries), str(tmp_path))
+            for name, entries in gen_golden.mount_cases(ns, str(tmp_path)).items()}
+    assert got == want
