@@ -29,7 +29,7 @@ from .blob_utils import FileUploadSpec, FileUploadSpec2, _ByteBudget
 from .exception import ExecutionError
 from .http_utils import ClientSessionRegistry
 
-VOLUME_PUT_FILE_CLIENT_TIMEOUT = 10 * 60  # seconds a single file may take to become visible (volume.py:77-79)
+VOLUME_PUT_FILE_CLIENT_TIMEOUT = 60 * 60  # seconds a single file may take to become visible (volume.py:79)
 
 
 class VolumeUploadTimeoutError(TimeoutError):
