@@ -31,12 +31,47 @@ def serialize_pickle(obj: Any) -> bytes:
     return cloudpickle.dumps(obj, protocol=4)
 
 
-def _function_fields(function) -> tuple[str | None, int, int]:
-    if getattr(function, "_metadata", True) is None:
+def get_preferred_payload_format(payload_format: str | None = None) -> int:
+    """``config.get("payload_format")`` of the reference (py/modal/_serialization.py:359-362; the setting is the
+    ``MODAL_PAYLOAD_FORMAT`` environment variable or the config file): "cbor" selects CBOR, anything else pickle."""
+    import os
+
+    fmt = (payload_format or os.environ.get("MODAL_PAYLOAD_FORMAT") or "pickle").lower()
+    return _wire.DATA_FORMAT_CBOR if fmt == "cbor" else _wire.DATA_FORMAT_PICKLE
+
+
+def serialize_data_format(obj: Any, data_format: int) -> bytes:
+    """The two argument formats of ``serialize_data_format`` (py/modal/_serialization.py:365-390)."""
+    if data_format == _wire.DATA_FORMAT_PICKLE:
+        return serialize_pickle(obj)
+    if data_format == _wire.DATA_FORMAT_CBOR:
+        try:
+            import cbor2
+        except ImportError:
+            raise ExecutionError("CBOR support requires the 'cbor2' package to be installed.")
+        try:
+            return cbor2.dumps(obj)
+        except cbor2.CBOREncodeError:
+            typename = f"{type(obj).__module__}.{type(obj).__name__}"
+            raise ExecutionError(f"Can not serialize type {typename} as cbor. If you need to use a custom data type, "
+                                 "try to serialize it yourself e.g. by using pickle.dumps(my_data)")
+    raise ExecutionError(f"Unknown data format {data_format!r}")
+
+
+def _function_fields(function, payload_format: str | None = None) -> tuple[str | None, int, int]:
+    """(method name, blob threshold, negotiated data format) as ``_create_input`` derives them (reference :589-601):
+    the preferred format if the function's metadata lists it, else the first format it supports (pickle when the
+    metadata lists none)."""
+    meta = getattr(function, "_metadata", True)
+    if not meta:
         raise ExecutionError("Attempted to call function that has not been hydrated with metadata")
     method_name = getattr(function, "_use_method_name", None) or None
     max_bytes = getattr(function, "_max_object_size_bytes", blob_utils.MAX_OBJECT_SIZE_BYTES)
-    return method_name, max_bytes, _wire.DATA_FORMAT_PICKLE
+    data_format = get_preferred_payload_format(payload_format)
+    supported = list(getattr(meta, "supported_input_formats", None) or []) or [_wire.DATA_FORMAT_PICKLE]
+    if data_format not in supported:
+        data_format = supported[0]
+    return method_name, max_bytes, data_format
 
 
 def _inline_item(idx: int, payload: bytes, data_format: int, method_name) -> "_wire.FunctionPutInputsItem":
@@ -55,9 +90,11 @@ def _blob_item(idx: int, upload: tuple[str, bool, int], data_format: int, method
 
 
 async def _create_input(args, kwargs, stub, *, function, idx: int | None = None, function_call_invocation_type=None,
-                        serializer: Callable[[Any], bytes] = serialize_pickle):
-    method_name, max_bytes, data_format = _function_fields(function)
-    payload = serializer((args, kwargs))
+                        serializer: Callable[[Any], bytes] | None = None, payload_format: str | None = None):
+    """Serialize ``(args, kwargs)`` in the negotiated format and build the FunctionPutInputsItem, uploading to blob
+    storage above the threshold (reference :576-621).  ``serializer`` overrides the format's serializer (tests)."""
+    method_name, max_bytes, data_format = _function_fields(function, payload_format)
+    payload = serializer((args, kwargs)) if serializer else serialize_data_format((args, kwargs), data_format)
     idx = idx or 0
     if should_upload(len(payload), max_bytes, function_call_invocation_type):
         upload = await blob_utils.blob_upload_with_r2_failure_info(payload, stub)
@@ -67,10 +104,10 @@ async def _create_input(args, kwargs, stub, *, function, idx: int | None = None,
 
 async def create_inputs_batch(argskwargs: Sequence[tuple[tuple, dict]], stub, *, function, first_idx: int = 0,
                               function_call_invocation_type=None,
-                              serializer: Callable[[Any], bytes] = serialize_pickle) -> list:
+                              serializer: Callable[[Any], bytes] | None = None, payload_format: str | None = None) -> list:
     """Items for inputs ``first_idx .. first_idx+len-1`` in order; all blobified payloads share one GPU batch."""
-    method_name, max_bytes, data_format = _function_fields(function)
-    payloads = [serializer(ak) for ak in argskwargs]
+    method_name, max_bytes, data_format = _function_fields(function, payload_format)
+    payloads = [serializer(ak) if serializer else serialize_data_format(ak, data_format) for ak in argskwargs]
     big = [i for i, p in enumerate(payloads) if should_upload(len(p), max_bytes, function_call_invocation_type)]
     uploads = dict(zip(big, await blob_utils.blob_upload_many([payloads[i] for i in big], stub))) if big else {}
     return [

@@ -84,3 +84,37 @@ def test_small_inputs_stay_inline(backend):
         assert one.idx == 2 and pickle.loads(one.input.args) == ((3,), {})
 
     asyncio.run(run())
+
+
+def test_payload_format_negotiation(backend, monkeypatch):
+    """_create_input's data-format choice (py/modal/_utils/function_utils.py:594-603): the preferred format when the
+    function supports it, else the first supported one, pickle when the metadata lists none; CBOR payloads are cbor2."""
+    import cbor2
+
+    PICKLE, CBOR = _wire.DATA_FORMAT_PICKLE, _wire.DATA_FORMAT_CBOR
+
+    def fn(supported):
+        return types.SimpleNamespace(_use_method_name="", _max_object_size_bytes=1 << 20,
+                                     _metadata=types.SimpleNamespace(supported_input_formats=supported), object_id="fu-1")
+
+    async def run():
+        stub = types.SimpleNamespace()  # nothing is uploaded: the payloads stay inline
+        item = await function_utils._create_input((1, "two"), {"k": [3]}, stub, function=fn([PICKLE, CBOR]), idx=7)
+        assert item.idx == 7 and item.input.data_format == PICKLE and pickle.loads(item.input.args) == ((1, "two"), {"k": [3]})
+        item = await function_utils._create_input((1, "two"), {"k": [3]}, stub, function=fn([PICKLE, CBOR]), payload_format="cbor")
+        assert item.input.data_format == CBOR and cbor2.loads(item.input.args) == [[1, "two"], {"k": [3]}]
+        item = await function_utils._create_input((1,), {}, stub, function=fn([PICKLE]), payload_format="cbor")
+        assert item.input.data_format == PICKLE                      # preferred format unsupported -> first supported
+        item = await function_utils._create_input((1,), {}, stub, function=fn([]), payload_format="cbor")
+        assert item.input.data_format == PICKLE                      # nothing listed -> pickle
+        monkeypatch.setenv("MODAL_PAYLOAD_FORMAT", "CBOR")
+        items = await function_utils.create_inputs_batch([((i,), {}) for i in range(3)], stub, function=fn([CBOR, PICKLE]))
+        assert [cbor2.loads(it.input.args) for it in items] == [[[i], {}] for i in range(3)]
+        assert all(it.input.data_format == CBOR for it in items)
+        with pytest.raises(function_utils.ExecutionError, match="as cbor"):
+            await function_utils._create_input((object(),), {}, stub, function=fn([CBOR]))
+        unhydrated = types.SimpleNamespace(_use_method_name="", _max_object_size_bytes=1, _metadata=None)
+        with pytest.raises(function_utils.ExecutionError, match="not been hydrated"):
+            await function_utils._create_input((), {}, stub, function=unhydrated)
+
+    asyncio.run(run())
