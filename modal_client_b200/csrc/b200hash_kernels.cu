@@ -331,6 +331,9 @@ __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], c
 #if B200H_ILV == 4
 #define QUAD(i, k0, k1, k2, k3, FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3) \
     SHA4(i, k0, k1, k2, k3) MD4(FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3)
+#elif B200H_ILV == 40  // MD5 steps ahead of the SHA rounds of the same quad
+#define QUAD(i, k0, k1, k2, k3, FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3) \
+    MD4(FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3) SHA4(i, k0, k1, k2, k3)
 #elif B200H_ILV == 2
 #define QUAD(i, k0, k1, k2, k3, FN, x0, x1, x2, x3, s0, s1, s2, s3, t0, t1, t2, t3) \
     SHA1(i, k0) SHA1((i) + 1, k1) MD1(0, FN, x0, s0, t0) MD1(1, FN, x1, s1, t1)     \
