@@ -100,3 +100,22 @@ def load():
     s = importlib.import_module("modal._utils.bytes_io_segment_payload")
     _loaded = (h, b, s)
     return _loaded
+
+
+def load_blob_utils_on(hash_utils_module):
+    """The reference's UNMODIFIED blob_utils.py executed with ``modal._utils.hash_utils`` replaced by
+    ``hash_utils_module`` -- i.e. the drop-in seam exercised from the reference's side: its own spec builders,
+    block gatherer and multipart code calling somebody else's ``get_upload_hashes``.  The substitution only
+    lasts for the import; the module returned is private (not left in sys.modules)."""
+    import importlib.util
+    from unittest import mock
+
+    load()  # stubs for modal.config / exception / async_utils / protobufs
+    path = os.path.join(package_dir(), "_utils", "blob_utils.py")
+    name = "modal._utils.blob_utils_dropin"
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = "modal._utils"
+    with mock.patch.dict(sys.modules, {"modal._utils.hash_utils": hash_utils_module, name: mod}):
+        spec.loader.exec_module(mod)
+    return mod
