@@ -129,6 +129,24 @@ def reference_hasher():
     return _REF
 
 
+def host_description() -> dict:
+    """What SURVEY 8(d) asks to be stated next to the CPU baseline: logical CPUs, CPU model, SHA extensions, OpenSSL."""
+    import ssl
+
+    model, sha_ni = "unknown", False
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name") and model == "unknown":
+                    model = line.split(":", 1)[1].strip()
+                elif line.startswith("flags"):
+                    sha_ni = " sha_ni" in line
+                    break
+    except OSError:
+        pass
+    return {"logical_cpus": os.cpu_count() or 1, "cpu_model": model, "sha_ni": sha_ni, "openssl": ssl.OPENSSL_VERSION}
+
+
 def run_cpu_pool(payloads: list[bytes], workers: int) -> float:
     from concurrent.futures import ThreadPoolExecutor
 
@@ -170,7 +188,7 @@ def run_reference(args) -> None:
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": round(gibs, 3), "unit": "GiB/s", "cores": workers, "kind": reference_hasher()[1],
-                         "sample": sample},
+                         "sample": sample, "host": host_description()},
         "e2e": {"value": round(gibs, 3), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -310,7 +328,8 @@ def run_gpu(args) -> None:
                          f"({'reference get_upload_hashes' if ref_kind == 'reference' else 'get_upload_hashes port'}), "
                          f"ThreadPool({workers})",
                "serial_value": round(serial_n * MSG_BYTES / GiB / serial_s, 3),
-               "serial_note": "one thread, as the reference's map pump really runs it (blob_utils.py:345)"}
+               "serial_note": "one thread, as the reference's map pump really runs it (blob_utils.py:345)",
+               "host": host_description()}
     ctx.host_free(host)
 
     if rank == 0:
