@@ -68,3 +68,36 @@ def test_reference_block_gatherer_on_our_hashes_reproduces_its_golden(ref_blob_o
                 io.BytesIO(data), PurePosixPath(c["path"]), asyncio.Semaphore(2), 0o644))
             assert [[b.start, b.end, b.contents_sha256.hex()] for b in spec.blocks] == c["blocks"]
             assert (spec.size, spec.mode, spec.path) == (c["size"], c["mode"], c["path"])
+
+
+def test_reference_multipart_upload_on_our_segment_payload(ref_blob_on_ours, monkeypatch):
+    """Second seam: the reference's UNMODIFIED perform_multipart_upload / _upload_to_s3_url (blob_utils.py:110-234)
+    driven with modal_client_b200's BytesIOSegmentPayload (per-part MD5 from the hash path).  The reference code itself
+    checks every part's ETag against `payload.md5_checksum().hexdigest()` and the assembled md5-of-md5s ETag, so the
+    upload only succeeds if our payload's digests are what hashlib's would have been."""
+    import sys
+    from unittest import mock
+
+    from modal_client_b200 import bytes_io_segment_payload as our_payload
+    from modal_client_b200.synth import synth_bytes
+    from tests.blob_server import running_blob_server
+
+    async def run():
+        async with running_blob_server() as (host, store):
+            data = synth_bytes(77, 10 * 1000 + 123)  # 11 parts of <= 1000 bytes
+            part_urls = [f"{host}/upload?blob_id=bl-x&part_number={i + 1}" for i in range(11)]
+            with mock.patch.dict(sys.modules, {"modal._utils.bytes_io_segment_payload": our_payload}):
+                await ref_blob_on_ours.perform_multipart_upload(
+                    io.BytesIO(data), content_length=len(data), max_part_size=1000, part_urls=part_urls,
+                    completion_url=f"{host}/complete_multipart?blob_id=bl-x", upload_chunk_size=256)
+            assert store.blobs["bl-x"] == data and len(store.parts["bl-x"]) == 11
+            # and a corrupted ETag from the server is caught by the reference's own check against our MD5
+            store.corrupt_etag = True
+            with mock.patch.dict(sys.modules, {"modal._utils.bytes_io_segment_payload": our_payload}):
+                with pytest.raises(Exception, match="checksum mismatch"):
+                    await ref_blob_on_ours.perform_multipart_upload(
+                        io.BytesIO(data), content_length=len(data), max_part_size=1000, part_urls=part_urls,
+                        completion_url=f"{host}/complete_multipart?blob_id=bl-x", upload_chunk_size=256)
+            await ref_blob_on_ours.ClientSessionRegistry.close_session()
+
+    asyncio.run(run())
