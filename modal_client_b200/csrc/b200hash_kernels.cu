@@ -749,9 +749,11 @@ lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
 // e / gridDim.x of CTA e % gridDim.x: up to gridDim.x outliers get an SM each, and with warp w of a CTA on SMSP
 // w % 4 the twelve warps of a full CTA put exactly one expander, one SHA-256 and one MD5 warp on every SMSP.
 
-constexpr int kChainGroups = 4;
+constexpr int kChainGroups = 4;     // messages per CTA by default (one expander, one SHA-256 and one MD5 warp per SMSP)
+constexpr int kChainGroupsMax = 8;  // B200H_CHAIN_GROUPS=8: twice that per SMSP -- built and parity-safe (same code, more
+                                    // groups), NOT yet measured against the lane kernel for 600-1 184 long messages
 constexpr int kChainGroupThreads = 96;
-constexpr int kChainThreads = kChainGroupThreads * kChainGroups;
+constexpr int kChainThreadsMax = kChainGroupThreads * kChainGroupsMax;
 constexpr int kTileBlocks = 32;
 constexpr int kTileData = kTileBlocks * 64;
 constexpr int kTileStride = kTileData + 32;  // + the misaligned leading granule; keeps 16-byte alignment
@@ -761,7 +763,10 @@ constexpr int kWkBuf = kTileBlocks * kWkRow;
 constexpr int kNW = 2;                        // W+K ring depth
 constexpr int kChainGroupSmem = (kNT * kTileStride + kNW * kWkBuf + (2 * kNT + 2 * kNW) * 8 + 127) & ~127;
 constexpr int kChainSmemMin = 116 * 1024;  // > 227 KB / 2: never two chain CTAs on one SM
-constexpr int kChainSmem = kChainGroups * kChainGroupSmem > kChainSmemMin ? kChainGroups * kChainGroupSmem : kChainSmemMin;
+constexpr int chain_smem_bytes(int groups) {
+    return groups * kChainGroupSmem > kChainSmemMin ? groups * kChainGroupSmem : kChainSmemMin;
+}
+static int g_chain_groups = kChainGroups;  // set once by configure_kernels() from B200H_CHAIN_GROUPS
 
 __constant__ uint32_t kShaKAll[64] = {
     0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
@@ -912,8 +917,8 @@ __device__ __forceinline__ void md5_chain_block(uint32_t (&hm)[4], const uint32_
     hm[0] += v[0]; hm[1] += v[1]; hm[2] += v[2]; hm[3] += v[3];
 }
 
-template <bool DO_SHA, bool DO_MD5>
-__global__ void __launch_bounds__(kChainThreads)
+template <bool DO_SHA, bool DO_MD5, int GROUPS>  // GROUPS only sets the launch bound (threads = 96 x GROUPS)
+__global__ void __launch_bounds__(kChainGroupThreads * GROUPS)
 chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
                   const uint32_t* __restrict__ chain_list, const int* __restrict__ qctl, uint32_t flags,
                   uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out, ChainState* __restrict__ st,
@@ -1390,15 +1395,22 @@ int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* 
     const uint32_t live = n_chain < kMaxChain ? n_chain : kMaxChain;
     const int grid = (int)(live < (uint32_t)g_sm_count ? live : (uint32_t)g_sm_count);
     if (grid <= 0) return 0;
-    if (s && m)
-        chain_hash_kernel<true, true><<<grid, kChainThreads, kChainSmem, st>>>(base, off, len, chain_list, qctl, flags,
-                                                                               sha_out, md5_out, state, resume, 1u);
-    else if (s)
-        chain_hash_kernel<true, false><<<grid, kChainThreads, kChainSmem, st>>>(base, off, len, chain_list, qctl, flags,
-                                                                                sha_out, md5_out, state, resume, 1u);
-    else if (m)
-        chain_hash_kernel<false, true><<<grid, kChainThreads, kChainSmem, st>>>(base, off, len, chain_list, qctl, flags,
-                                                                                sha_out, md5_out, state, resume, 1u);
+    const int groups = (int)((live + grid - 1) / grid) <= kChainGroups ? kChainGroups : kChainGroupsMax;
+    const int threads = kChainGroupThreads * groups, smem = chain_smem_bytes(groups);
+#define CHAIN_LAUNCH(S_, M_)                                                                                          \
+    do {                                                                                                              \
+        if (groups == kChainGroups)                                                                                   \
+            chain_hash_kernel<S_, M_, kChainGroups><<<grid, threads, smem, st>>>(base, off, len, chain_list, qctl, flags, \
+                                                                                 sha_out, md5_out, state, resume, 1u);  \
+        else                                                                                                          \
+            chain_hash_kernel<S_, M_, kChainGroupsMax><<<grid, threads, smem, st>>>(base, off, len, chain_list, qctl,  \
+                                                                                    flags, sha_out, md5_out, state,   \
+                                                                                    resume, 1u);                      \
+    } while (0)
+    if (s && m) CHAIN_LAUNCH(true, true);
+    else if (s) CHAIN_LAUNCH(true, false);
+    else if (m) CHAIN_LAUNCH(false, true);
+#undef CHAIN_LAUNCH
     else
         return 0;
     return 1;
@@ -1463,10 +1475,11 @@ int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t sta
     return 1;
 }
 
-int chain_groups_per_cta() { return kChainGroups; }
+int chain_groups_per_cta() { return g_chain_groups; }
 
 cudaError_t configure_kernels() {
     cudaError_t e;
+    if (const char* g = getenv("B200H_CHAIN_GROUPS")) g_chain_groups = atoi(g) >= kChainGroupsMax ? kChainGroupsMax : kChainGroups;
     const void* lane_kernels[5] = {(const void*)lane_hash_kernel<true, true, false>, (const void*)lane_hash_kernel<true, false, false>,
                                    (const void*)lane_hash_kernel<false, true, false>, (const void*)lane_hash_kernel<true, true, true>,
                                    (const void*)lane_hash_kernel<true, false, true>};
@@ -1474,12 +1487,15 @@ cudaError_t configure_kernels() {
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem);
         if (e != cudaSuccess) return e;
     }
-    e = cudaFuncSetAttribute(chain_hash_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(chain_hash_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(chain_hash_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem);
-    if (e != cudaSuccess) return e;
+    const void* chain_kernels[6] = {
+        (const void*)chain_hash_kernel<true, true, kChainGroups>, (const void*)chain_hash_kernel<true, false, kChainGroups>,
+        (const void*)chain_hash_kernel<false, true, kChainGroups>, (const void*)chain_hash_kernel<true, true, kChainGroupsMax>,
+        (const void*)chain_hash_kernel<true, false, kChainGroupsMax>, (const void*)chain_hash_kernel<false, true, kChainGroupsMax>};
+    for (int i = 0; i < 6; ++i) {
+        e = cudaFuncSetAttribute(chain_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 chain_smem_bytes(i < 3 ? kChainGroups : kChainGroupsMax));
+        if (e != cudaSuccess) return e;
+    }
     int dev = 0, sms = 0, ctas = 0;
     e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
