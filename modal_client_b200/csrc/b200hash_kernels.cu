@@ -750,8 +750,8 @@ lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
 // w % 4 the twelve warps of a full CTA put exactly one expander, one SHA-256 and one MD5 warp on every SMSP.
 
 constexpr int kChainGroups = 4;     // messages per CTA by default (one expander, one SHA-256 and one MD5 warp per SMSP)
-constexpr int kChainGroupsMax = 8;  // B200H_CHAIN_GROUPS=8: twice that per SMSP -- built and parity-safe (same code, more
-                                    // groups), NOT yet measured against the lane kernel for 600-1 184 long messages
+constexpr int kChainGroupsMax = 8;  // B200H_CHAIN_GROUPS=8: twice that per SMSP -- measured: no gain over packed lanes (same code, more
+                                    // groups) except for MD5-only sets, profiles/r1_outlier_chain.md; off by default
 constexpr int kChainGroupThreads = 96;
 constexpr int kChainThreadsMax = kChainGroupThreads * kChainGroupsMax;
 constexpr int kTileBlocks = 32;
