@@ -6,12 +6,16 @@ Workload (BASELINE.json configs[1]): the Function.map input pump -- 100 000 pick
 independent, no data-path collective; the per-rank digest tables are all-gathered over NCCL).
 
   value     GiB/s with the payloads already resident in HBM (CUDA events, max over ranks)
-  e2e       GiB/s through the public API on page-locked HOST buffers (H2D + kernels + D2H digests)
+  e2e       GiB/s through the plugin call itself: 100 000 pageable Python ``bytes`` -> parallel_map.InputPreprocessor
+            (one GPU hash batch per byte-budgeted window, pack + H2D + kernels + D2H digests) -> BlobCreate / PUT per
+            input -> parallel_map.InputPumper, against a null control plane / object store
+  e2e_pinned  the same payloads through batch.hash_table_host on page-locked host memory (round 1's e2e figure)
   roofline  lane_hash_kernel: algorithmic bytes / measured kernel time vs the measured HBM copy peak
-  cpu_baseline  the reference's hashlib path (oracle/ref_port.py) on the host cores, bounded sample
+  cpu_baseline  the reference's own get_upload_hashes (unmodified hash_utils.py from baseline/_ref through
+            oracle/ref_shim.py; oracle/ref_port.py only if that copy is missing) on the host cores, bounded sample
 
-`--impl reference` times the reference's own CPU implementation (hashlib via oracle/ref_port.py,
-all host threads) on the same workload shape and prints the same JSON line.
+`--impl reference` times that same reference implementation (hashlib underneath, all host threads) on the same
+workload shape and prints the same JSON line.
 """
 from __future__ import annotations
 
@@ -196,19 +200,94 @@ def run_reference(args) -> None:
 # ----------------------------------------------------------------------------------------- GPU arm
 
 
+class _NullBlobResponse:
+    """What BlobCreate answers for a single-part upload (modal_proto/api.proto BlobCreateResponse): one blob id and
+    one pre-signed URL.  The null stub hands the same object back for every request."""
+
+    blob_ids = ["bl-null"]
+
+    class _Urls:
+        items = ["null://put"]
+
+    upload_urls = _Urls()
+
+    def WhichOneof(self, _name):
+        return "upload_urls"
+
+
+class NullStub:
+    """Control plane + object store that cost nothing: BlobCreate keeps the request (so the digests the pump
+    computed can be checked afterwards), FunctionPutInputs counts items."""
+
+    def __init__(self):
+        self.blob_requests = []
+        self.inputs_put = 0
+        self._resp = _NullBlobResponse()
+
+    async def BlobCreate(self, request):
+        self.blob_requests.append(request)
+        return self._resp
+
+    async def FunctionPutInputs(self, request):
+        self.inputs_put += len(request.inputs)
+
+
+async def _null_put(upload_url, payload, content_md5_b64=None, content_type="application/octet-stream"):
+    """Stand-in for blob_utils._upload_to_s3_url: the payload object is built and handed over, no byte leaves."""
+    return payload.md5_checksum().hexdigest()
+
+
+def run_map_pump(payloads, stub) -> float:
+    """One pass of the REAL plugin path over pageable ``bytes``: parallel_map.InputPreprocessor (collect -> one GPU
+    hash batch per window -> BlobCreate + PUT per input) feeding parallel_map.InputPumper, as Function.map drives
+    them (py/modal/parallel_map.py:90-198, _utils/blob_utils.py:338-352).  The inputs are already in wire format
+    (``serializer`` = identity: "pickled inputs"), every one above the blob threshold.  Returns seconds."""
+    import asyncio
+    import types
+
+    from modal_client_b200 import parallel_map
+
+    fn = types.SimpleNamespace(_use_method_name="", _max_object_size_bytes=1, _metadata=object(), object_id="fu-bench")
+    client = types.SimpleNamespace(stub=stub)
+
+    async def main():
+        raw, done = asyncio.Queue(), asyncio.Queue()
+        for p in payloads:
+            raw.put_nowait(p)
+        raw.put_nowait(None)
+        pre = parallel_map.InputPreprocessor(client, raw_input_queue=raw, processed_input_queue=done, function=fn,
+                                             serializer=lambda p: p)
+        pre.keep_digest_tables = True  # the per-window (sha, md5) tables, for the multi-GPU all-gather
+        pump = parallel_map.InputPumper(client, input_queue=done, function=fn, function_call_id="fc-bench")
+
+        async def drive(gen):
+            async for _ in gen:
+                pass
+
+        t0 = time.perf_counter()
+        await asyncio.gather(drive(pre.drain_input_generator()), drive(pump.pump_inputs()))
+        dt = time.perf_counter() - t0
+        assert pump.inputs_sent == len(payloads)
+        return dt, pre.hash_batches, pre.digest_tables
+
+    return asyncio.run(main())
+
+
 def run_gpu(args) -> None:
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from modal_client_b200 import _lib, batch, sharding
+    from modal_client_b200 import _backend, _lib, batch, blob_utils, parallel_map, sharding
 
     rank, world, local_rank = env_rank()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)  # the gather slips in between hash kernels
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     ctx = _lib.Context(local_rank, pinned_bytes=512 << 20, device_bytes=8 << 30)
+    _backend.set_context(ctx)
     BOTH = _lib.SHA256 | _lib.MD5
     total_bytes = N_MSG * MSG_BYTES
     seed = 0xB200 + rank
@@ -218,21 +297,38 @@ def run_gpu(args) -> None:
     ctx.fill_synth_device(data.data_ptr(), total_bytes, seed)
     off = torch.arange(N_MSG, dtype=torch.int64, device=dev) * MSG_BYTES
     ln = torch.full((N_MSG,), MSG_BYTES, dtype=torch.int64, device=dev)
-    sha = torch.empty((N_MSG, 32), dtype=torch.uint8, device=dev)
-    md5 = torch.empty((N_MSG, 16), dtype=torch.uint8, device=dev)
-    if world > 1:
-        sha_all = torch.empty((world * N_MSG, 32), dtype=torch.uint8, device=dev)
-        md5_all = torch.empty((world * N_MSG, 16), dtype=torch.uint8, device=dev)
+    len_h = np.full(N_MSG, MSG_BYTES, dtype=np.uint64)  # the lengths on the host: the hash call then only enqueues
+    # ONE packed digest table per step: n x 32 SHA-256 rows followed by n x 16 MD5 rows (48 B per message), double
+    # buffered so that the all-gather of step k (side stream) overlaps the hash kernel of step k+1.
+    NBUF = 2
+    tabs = [torch.empty(N_MSG * 48, dtype=torch.uint8, device=dev) for _ in range(NBUF)]
+    gathered = [torch.empty(world * N_MSG * 48, dtype=torch.uint8, device=dev) for _ in range(NBUF)] if world > 1 else None
     stream = torch.cuda.Stream(device=dev)  # non-default stream: the library launches on this very handle
+    side = torch.cuda.Stream(device=dev)
+    hashed = [torch.cuda.Event() for _ in range(NBUF)]
+    gathered_ev = [torch.cuda.Event() for _ in range(NBUF)]
     torch.cuda.set_stream(stream)
     torch.cuda.synchronize()
+    step_no = [0]
 
     def step():
-        ctx.hash_batch_device(data.data_ptr(), off.data_ptr(), ln.data_ptr(), N_MSG, BOTH, sha.data_ptr(), md5.data_ptr(),
-                              0, stream.cuda_stream)
-        if world > 1:  # the path's only exchange: all-gather of the fixed-width digest table
-            dist.all_gather_into_tensor(sha_all, sha)
-            dist.all_gather_into_tensor(md5_all, md5)
+        b = step_no[0] % NBUF
+        step_no[0] += 1
+        tab = tabs[b]
+        if world > 1 and step_no[0] > NBUF:
+            stream.wait_event(gathered_ev[b])  # the gather that last read this buffer
+        ctx.hash_batch_device(data.data_ptr(), off.data_ptr(), ln.data_ptr(), N_MSG, BOTH, tab.data_ptr(),
+                              tab.data_ptr() + 32 * N_MSG, 0, stream.cuda_stream, h_lengths=len_h)
+        if world > 1:  # the path's only exchange: all-gather of the fixed-width digest table, off the hash stream
+            hashed[b].record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(hashed[b])
+                dist.all_gather_into_tensor(gathered[b], tab)
+                gathered_ev[b].record(side)
+
+    def drain():
+        if world > 1:
+            stream.wait_stream(side)
 
     def barrier():
         if world > 1:
@@ -241,83 +337,140 @@ def run_gpu(args) -> None:
 
     for _ in range(args.warmup):
         step()
+    drain()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count
+    syncs0 = ctx.plan_sync_count
     ctx.profile_enable(True)
     ctx.profile_read()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
         step()
+    drain()
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
     kern_ms, kern_n = ctx.profile_read()
     ctx.profile_enable(False)
     launches = ctx.launch_count - launches0
+    plan_syncs = ctx.plan_sync_count - syncs0
     clock_rows = sampler.halt() if rank == 0 else []
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * total_bytes * args.steps / GiB / (ms / 1e3)
+    last = tabs[(step_no[0] - 1) % NBUF].cpu().numpy()
+    sha_dev, md5_dev = last[: 32 * N_MSG].reshape(-1, 32), last[32 * N_MSG :].reshape(-1, 16)
+    gather_ok = None
+    if world > 1:  # every rank holds every rank's table: this rank's slice must be its own table
+        g = gathered[(step_no[0] - 1) % NBUF]
+        gather_ok = bool(torch.equal(g[rank * N_MSG * 48 : (rank + 1) * N_MSG * 48], tabs[(step_no[0] - 1) % NBUF]))
 
-    # ---- end to end through the public API on page-locked host buffers
+    # ---- (secondary) end to end on page-locked host buffers: hash_table_host, digests to host
     host = ctx.host_alloc(total_bytes)
     torch.from_numpy(host).copy_(data)  # host bytes == device bytes
     torch.cuda.synchronize()
+    del data
+    torch.cuda.empty_cache()
     off_h = (np.arange(N_MSG, dtype=np.uint64) * np.uint64(MSG_BYTES))
-    len_h = np.full(N_MSG, MSG_BYTES, dtype=np.uint64)
     e2e_steps = max(1, min(args.steps, 3))
-    def e2e_step():
-        tab = batch.hash_table_host(host, off_h, len_h, ctx=ctx)
+    e2e_warm = max(1, min(args.warmup, 3))
+
+    def all_gather_host_table(packed: np.ndarray):
         if world > 1:  # every rank ends the step holding the whole job's digest table
-            sharding.all_gather_table(tab.packed(), [N_MSG] * world, device=dev)
+            sharding.all_gather_table(packed, [N_MSG] * world, device=dev)
+
+    def pinned_step():
+        tab = batch.hash_table_host(host, off_h, len_h, ctx=ctx)
+        all_gather_host_table(tab.packed())
         return tab
 
-    for _ in range(max(1, min(args.warmup, 3))):  # warm-up (first call allocates the wave buffers)
-        table = e2e_step()
+    for _ in range(e2e_warm):  # warm-up (first call allocates the wave buffers)
+        table = pinned_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        table = pinned_step()
+    barrier()
+    pinned_s = time.perf_counter() - t0
+    same = bool(np.array_equal(table.sha256, sha_dev) and np.array_equal(table.md5, md5_dev))
+
+    # ---- (headline) end to end through the plugin call: pageable bytes -> map input pump -> BlobCreate/PUT (null)
+    payloads = [host[i * MSG_BYTES:(i + 1) * MSG_BYTES].tobytes() for i in range(N_MSG)]  # ordinary Python bytes
+    ctx.host_free(host)
+    blob_utils._upload_to_s3_url = _null_put
+    launches_pump0 = ctx.launch_count
+
+    def pump_step():
+        stub = NullStub()
+        dt, batches, tables = run_map_pump(payloads, stub)
+        return stub, dt, batches, tables
+
+    def pump_table(tables) -> np.ndarray:
+        """uint8[n, 48] digest table of one pump pass, from the per-window tables the preprocessor kept."""
+        sha = np.concatenate([t[0] for t in tables])
+        md5 = np.concatenate([t[1] for t in tables])
+        return np.concatenate([sha, md5], axis=1)
+
+    def requests_table(stub) -> np.ndarray:
+        """The same table as the control plane received it (base64 fields of the BlobCreate requests)."""
+        import base64
+
+        rows = [base64.b64decode(r.content_sha256_base64) + base64.b64decode(r.content_md5) for r in stub.blob_requests]
+        return np.frombuffer(b"".join(rows), np.uint8).reshape(-1, 48)
+
+    for _ in range(e2e_warm):
+        pump_step()
     barrier()
     sampler2 = ClockSampler(local_rank)
     if rank == 0:
         sampler2.start()
     t0 = time.perf_counter()
+    pump_batches = 0
     for _ in range(e2e_steps):
-        table = e2e_step()
+        stub, _dt, pump_batches, tables = pump_step()
+        if world > 1:
+            all_gather_host_table(pump_table(tables))
     barrier()
-    e2e_s = time.perf_counter() - t0
+    pump_s = time.perf_counter() - t0
+    pump_launches = (ctx.launch_count - launches_pump0)
     clocks = None
-    if rank == 0:  # clocks sampled inside the two timed regions only (HBM-resident steps and e2e steps)
+    if rank == 0:  # clocks sampled inside the timed regions (HBM-resident steps and the headline e2e steps)
         clocks = ClockSampler.summarize(clock_rows + sampler2.halt(), sampler.proc is not None)
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([pinned_s, pump_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = world * total_bytes * e2e_steps / GiB / e2e_s
-    # property check: host path and HBM-resident path produce the same digest table
-    same = bool(np.array_equal(table.sha256, sha.cpu().numpy()) and np.array_equal(table.md5, md5.cpu().numpy()))
+    pinned_s, pump_s = float(t[0].item()), float(t[1].item())
+    pinned_value = world * total_bytes * e2e_steps / GiB / pinned_s
+    pump_value = world * total_bytes * e2e_steps / GiB / pump_s
+    ptab = requests_table(stub)  # what BlobCreate was told, checked after the timed region
+    pump_same = bool(len(ptab) == N_MSG and np.array_equal(ptab[:, :32], sha_dev) and np.array_equal(ptab[:, 32:], md5_dev))
 
     # ---- CPU baseline (rank 0, N=1): the reference's hashlib path on a bounded sample of the same bytes
     cpu = None
-    parity = "host==device tables: %s" % ("exact" if same else "MISMATCH")
+    parity = "tables device==pinned-host: %s; device==map-pump: %s" % ("exact" if same else "MISMATCH",
+                                                                        "exact" if pump_same else "MISMATCH")
+    if gather_ok is not None:
+        parity += "; all-gathered slice == own table: %s" % ("exact" if gather_ok else "MISMATCH")
     if rank == 0 and world == 1:
-        sample_n = int(os.environ.get("B200H_CPU_SAMPLE", 16384))
-        sample_n = min(sample_n, N_MSG)
-        payloads = [host[i * MSG_BYTES:(i + 1) * MSG_BYTES].tobytes() for i in range(sample_n)]
+        sample_n = min(int(os.environ.get("B200H_CPU_SAMPLE", 16384)), N_MSG)
+        sample = payloads[:sample_n]
         from concurrent.futures import ThreadPoolExecutor
 
         ref_fn, ref_kind = reference_hasher()
-        workers = best_pool_workers(payloads[:4096])
+        workers = best_pool_workers(sample[:4096])
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=workers) as ex:
-            hashes = list(ex.map(ref_fn, payloads))
+            hashes = list(ex.map(ref_fn, sample))
         pool_s = time.perf_counter() - t0
         serial_n = min(2048, sample_n)
         t0 = time.perf_counter()
-        for p_ in payloads[:serial_n]:
+        for p_ in sample[:serial_n]:
             ref_fn(p_)
         serial_s = time.perf_counter() - t0
         ok = all(h.sha256_hex() == table.sha256_hex(i) and h.md5_hex() == table.md5_hex(i)
@@ -330,7 +483,6 @@ def run_gpu(args) -> None:
                "serial_value": round(serial_n * MSG_BYTES / GiB / serial_s, 3),
                "serial_note": "one thread, as the reference's map pump really runs it (blob_utils.py:345)",
                "host": host_description()}
-    ctx.host_free(host)
 
     if rank == 0:
         peak, peak_src = hbm_peak_gbs()
@@ -348,7 +500,9 @@ def run_gpu(args) -> None:
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "bytes_per_gpu_per_step": total_bytes, "digests": "sha256+md5 fused",
                        "l2": "inputs (24.4 GiB/GPU) larger than L2, no flush needed", "parallelism": f"shard{world}",
-                       "collective": "nccl all_gather of digest table" if world > 1 else "none"},
+                       "collective": ("nccl all_gather of ONE packed 48-B-row digest table per step on a side stream, "
+                                      "double buffered (gather k overlaps hash k+1)") if world > 1 else "none",
+                       "host_syncs_in_timed_region": int(plan_syncs)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "lane_hash_kernel<sha256,md5>",
@@ -357,13 +511,22 @@ def run_gpu(args) -> None:
                          "note": "hbm frac per the contract; the binding limit is INT32 issue: 1168 ALU-pipe instr per "
                                  "64 B block at 0.5 warp-instr/clk/SMSP x 592 SMSP x 1.965 GHz = 1018 GB/s (DESIGN.md 5.1)"},
             "cpu_baseline": cpu,
-            "e2e": {"value": round(e2e_value, 3), "unit": "GiB/s", "h2d_bytes_per_step": total_bytes + 16 * N_MSG,
+            "e2e": {"value": round(pump_value, 3), "unit": "GiB/s", "h2d_bytes_per_step": total_bytes + 16 * N_MSG,
                     "d2h_bytes_per_step": 56 * N_MSG, "steps": e2e_steps,
-                    "api": "modal_client_b200.batch.hash_table_host on page-locked host memory"
-                           + (" + sharding.all_gather_table (NCCL)" if world > 1 else "")},
+                    "api": "parallel_map.InputPreprocessor -> hash_utils.get_upload_hashes_many -> blob_utils._blob_upload "
+                           "-> parallel_map.InputPumper over 100 000 pageable Python bytes (wire-format inputs, identity "
+                           "serializer), null BlobCreate / PUT / FunctionPutInputs"
+                           + (" + sharding.all_gather_table (NCCL)" if world > 1 else ""),
+                    "hash_batches_per_step": pump_batches,
+                    "window_bytes": parallel_map.HASH_WINDOW_BYTES, "windows_in_flight": parallel_map.HASH_WINDOWS_IN_FLIGHT,
+                    "gpu_launches": int(pump_launches)},
+            "e2e_pinned": {"value": round(pinned_value, 3), "unit": "GiB/s", "steps": e2e_steps,
+                           "api": "batch.hash_table_host on page-locked host memory (one call, 100 000 messages)"
+                                  + (" + sharding.all_gather_table (NCCL)" if world > 1 else "")},
             "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
         }
         print(json.dumps(out))
+    _backend.set_context(None)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

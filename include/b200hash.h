@@ -10,8 +10,11 @@
  *   - every function returning int returns 0 on success and a negative B200H_E_* code on failure;
  *     b200h_last_error(ctx) gives a message (owned by the library, valid until the next call on ctx);
  *   - no exceptions cross the boundary; the caller owns every buffer it passes;
- *   - a context is bound to one CUDA device; calls on one context are serialised internally
- *     (thread-safe, re-entrant across contexts); the caller's GIL is never needed;
+ *   - a context is bound to one CUDA device; batch calls on one context are serialised internally
+ *     (thread-safe, re-entrant across contexts); the caller's GIL is never needed.  Concurrent SMALL
+ *     b200h_hash_batch_host calls (<= 1024 messages each) are merged into one GPU batch by a combining queue
+ *     (the first caller in leads, the others ride along and get their own rows back), and every b200h_stream
+ *     runs on its own CUDA stream, so the reference's thread-pool callers overlap on the GPU;
  *   - there is NO CPU fallback: without a usable CUDA device b200h_create fails with B200H_E_CUDA.
  *   - digests are raw bytes: SHA-256 = 32 bytes (big-endian words, FIPS 180-4), MD5 = 16 bytes (RFC 1321).
  */
@@ -28,6 +31,8 @@ extern "C" {
 #define B200H_SHA256 1u     /* compute SHA-256 */
 #define B200H_MD5 2u        /* compute MD5 */
 #define B200H_TRIM_ZEROS 4u /* hash the prefix up to the last non-zero byte (volumefs2 blocks) */
+#define B200H_NO_OUTLIERS 16u /* keep every message on the lane kernel (no outlier routing): with it
+                                 b200h_hash_batch_device never reads anything back, i.e. only enqueues */
 
 #define B200H_OK 0
 #define B200H_E_INVALID (-1) /* bad argument */
@@ -62,7 +67,8 @@ void b200h_host_free(b200h_ctx* ctx, void* p);
  * (base may be NULL with absolute addresses in offsets[].)  Outputs (each may be NULL): sha256_out[n*32],
  * md5_out[n*16], trimmed_len_out[n] (length actually hashed; == lengths[i] unless B200H_TRIM_ZEROS).
  * Stages through pinned memory to HBM with cudaMemcpyAsync in double-buffered waves; blocks until the
- * digests are in the output arrays.
+ * digests are in the output arrays.  The output arrays may be host or device memory (copied with
+ * cudaMemcpyDefault): a caller that all-gathers the table over NCCL next passes device buffers.
  * Replaces: hashlib in hash_utils.get_upload_hashes (py/modal/_utils/hash_utils.py:68-101) as called per
  * payload from blob_utils.py:345 (map pump) and per file from blob_utils.py:459-474 (FileUploadSpec);
  * with B200H_TRIM_ZEROS: _find_end_of_block + _hash_range_sha256 (blob_utils.py:640-705);
@@ -73,11 +79,21 @@ int b200h_hash_batch_host(b200h_ctx* ctx, const uint8_t* base, const uint64_t* o
 
 /* Same, but every pointer is a DEVICE pointer on ctx's device and the call only enqueues work on
  * `cuda_stream` (a cudaStream_t; NULL = the context's compute stream).  d_sha256/d_md5 must be 16-byte
- * aligned.  This is the HBM-resident path the roofline is quoted on.  (The call synchronises `cuda_stream` once,
- * briefly, after the ~12 us planning kernels, to read how many outlier messages go to the chain kernel.) */
+ * aligned.  This is the HBM-resident path the roofline is quoted on.
+ * Outlier routing (a few very long messages go to the chain kernel, whose launch is sized on the host) needs the
+ * planner's count.  Three ways, in order of preference:
+ *   b200h_hash_batch_device_hl  the caller also holds the lengths on the host (h_lengths[n] == d_lengths[n]): the
+ *                               library computes the same selection there; the call ONLY ENQUEUES;
+ *   flags | B200H_NO_OUTLIERS   no outlier routing for this batch (right for many similar messages); ONLY ENQUEUES;
+ *   neither                     the count is read back after the ~12 us planning kernels: one synchronisation of
+ *                               `cuda_stream` per call (also whenever B200H_TRIM_ZEROS is set and outliers are on:
+ *                               the lengths that matter then exist on the device only). */
 int b200h_hash_batch_device(b200h_ctx* ctx, const void* d_base, const uint64_t* d_offsets, const uint64_t* d_lengths,
                             uint64_t n, uint32_t flags, void* d_sha256, void* d_md5, uint64_t* d_trimmed_len,
                             void* cuda_stream);
+int b200h_hash_batch_device_hl(b200h_ctx* ctx, const void* d_base, const uint64_t* d_offsets, const uint64_t* d_lengths,
+                               const uint64_t* h_lengths, uint64_t n, uint32_t flags, void* d_sha256, void* d_md5,
+                               uint64_t* d_trimmed_len, void* cuda_stream);
 
 /* Split one host buffer into ceil(len/part_len) fixed-size parts and hash each (the last may be short).
  * etag_md5_out (may be NULL) = MD5 over the concatenated raw part MD5s, computed on the device
@@ -109,7 +125,10 @@ int b200h_hash_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, const
 
 /* Incremental digest of ONE message fed in arbitrary pieces with bounded memory; the chaining state
  * stays on the device between updates.  A single message is a serial Merkle-Damgard chain, so this is
- * latency-bound by construction -- use the batch entry points for throughput.
+ * latency-bound by construction (~70 MB/s per stream) -- use the batch entry points for throughput.
+ * update() gathers into a pinned buffer and enqueues one absorb per 4 MiB (B200H_STREAM_BUF) without waiting
+ * for it; every stream has its own CUDA stream and scratch, so N streams fed from N threads advance concurrently.
+ * One stream object must not be used from two threads at once (like a hashlib object).
  * Replaces: hashlib objects in hash_utils._update over a BinaryIO (hash_utils.py:18-29) and
  * BytesIOSegmentPayload._md5_checksum (bytes_io_segment_payload.py:58,102,79-80). */
 int b200h_stream_new(b200h_ctx* ctx, uint32_t flags, b200h_stream** out);
@@ -145,6 +164,12 @@ int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64
 int b200h_last_outlier_count(b200h_ctx* ctx, uint32_t* count_out);
 /* Kernels launched by this context so far (all kinds). */
 uint64_t b200h_launch_count(b200h_ctx* ctx);
+/* Combining queue of b200h_hash_batch_host: GPU batches issued for, and caller requests served by, the small-request
+ * path so far (requests / groups = how many concurrent callers shared a batch on average). */
+int b200h_combine_stats(b200h_ctx* ctx, uint64_t* groups_out, uint64_t* requests_out);
+/* Enqueues that had to synchronise their stream to read the planner's outlier count back (see
+ * b200h_hash_batch_device); 0 for a caller that passes host lengths or B200H_NO_OUTLIERS. */
+uint64_t b200h_plan_sync_count(b200h_ctx* ctx);
 /* When enabled, every lane_hash launch is bracketed by CUDA events on its stream;
  * b200h_profile_read synchronises and returns the accumulated device time and launch count, then clears. */
 int b200h_profile_enable(b200h_ctx* ctx, int on);

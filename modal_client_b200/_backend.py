@@ -20,3 +20,21 @@ def set_context(ctx) -> None:
 
 def get_context():
     return _override if _override is not None else _lib.default_context()
+
+
+_pool: list = []
+
+
+def context_pool(n: int) -> list:
+    """``n`` contexts on this process's device for callers that keep several host batches in flight (the map pump
+    hashes window k+1 while window k's tail is still on the GPU): the current context plus ``n-1`` more on the same
+    device, created on first use.  A stand-in installed by the tests is returned ``n`` times."""
+    first = get_context()
+    if not isinstance(first, _lib.Context):
+        return [first] * n
+    while len(_pool) < n - 1 or any(c.device != first.device or not getattr(c, "_h", None) for c in _pool):
+        _pool[:] = [c for c in _pool if c.device == first.device and getattr(c, "_h", None)]
+        if len(_pool) >= n - 1:
+            break
+        _pool.append(_lib.Context(first.device))
+    return [first] + _pool[: n - 1]

@@ -21,6 +21,7 @@ CSRC = os.path.join(_PKG, "csrc")
 SHA256 = 1
 MD5 = 2
 TRIM_ZEROS = 4
+NO_OUTLIERS = 16  # keep every message on the lane kernel: device batches then only enqueue (include/b200hash.h)
 
 #: every symbol include/b200hash.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = (
@@ -29,7 +30,7 @@ ABI_SYMBOLS = (
     "b200h_hash_fixed_parts", "b200h_stat_files", "b200h_hash_files", "b200h_stream_new", "b200h_stream_update", "b200h_stream_digest",
     "b200h_stream_reset", "b200h_stream_free", "b200h_fill_synth_device", "b200h_launch_count",
     "b200h_profile_enable", "b200h_profile_read", "b200h_dedupe_host", "b200h_dedupe_device",
-    "b200h_last_outlier_count",
+    "b200h_last_outlier_count", "b200h_hash_batch_device_hl", "b200h_combine_stats", "b200h_plan_sync_count",
 )
 
 
@@ -87,6 +88,12 @@ def load_library() -> ctypes.CDLL:
         L.b200h_hash_batch_host.restype = i32
         L.b200h_hash_batch_device.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, vp, vp]
         L.b200h_hash_batch_device.restype = i32
+        L.b200h_hash_batch_device_hl.argtypes = [vp, vp, vp, vp, vp, u64, u32, vp, vp, vp, vp]
+        L.b200h_hash_batch_device_hl.restype = i32
+        L.b200h_combine_stats.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+        L.b200h_combine_stats.restype = i32
+        L.b200h_plan_sync_count.argtypes = [vp]
+        L.b200h_plan_sync_count.restype = u64
         L.b200h_hash_fixed_parts.argtypes = [vp, vp, u64, u64, u32, vp, vp, vp, vp, ctypes.POINTER(u64)]
         L.b200h_hash_fixed_parts.restype = i32
         L.b200h_stat_files.argtypes = [vp, vp, u64, vp, vp]
@@ -173,6 +180,17 @@ class Context:
         self._check(self._L.b200h_last_outlier_count(self._h, ctypes.byref(c)), "b200h_last_outlier_count")
         return int(c.value)
 
+    @property
+    def plan_sync_count(self) -> int:
+        """Enqueues that had to synchronise their stream to read the planner's outlier count back."""
+        return int(self._L.b200h_plan_sync_count(self._h))
+
+    def combine_stats(self) -> tuple[int, int]:
+        """(GPU batches issued, caller requests served) by the combining queue of small hash_batch_host calls."""
+        g, r = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self._L.b200h_combine_stats(self._h, ctypes.byref(g), ctypes.byref(r)), "b200h_combine_stats")
+        return int(g.value), int(r.value)
+
     def profile_enable(self, on: bool = True):
         self._check(self._L.b200h_profile_enable(self._h, int(on)), "b200h_profile_enable")
 
@@ -201,9 +219,12 @@ class Context:
             self._L.b200h_host_free(self._h, p)
 
     # -- batch over host memory
-    def hash_batch_host(self, base, offsets, lengths, flags: int = SHA256 | MD5):
+    def hash_batch_host(self, base, offsets, lengths, flags: int = SHA256 | MD5, *, out_sha: int = 0, out_md5: int = 0,
+                        out_trimmed: int = 0):
         """base: uint8 ndarray / bytes-like / int address / None (absolute addresses in offsets).
-        -> (sha[n,32] | None, md5[n,16] | None, trimmed[n])"""
+        -> (sha[n,32] | None, md5[n,16] | None, trimmed[n])
+        out_sha / out_md5 / out_trimmed: raw addresses (host or DEVICE memory, e.g. a CUDA tensor's data_ptr()) that
+        receive the columns instead of fresh numpy arrays; the corresponding element of the result is then None."""
         off = np.ascontiguousarray(offsets, dtype=np.uint64)
         ln = np.ascontiguousarray(lengths, dtype=np.uint64)
         n = int(off.size)
@@ -219,11 +240,13 @@ class Context:
         else:
             keep = np.frombuffer(base, dtype=np.uint8)
             bp = ctypes.c_void_p(keep.ctypes.data) if keep.size else ctypes.c_void_p(off.ctypes.data)
-        sha = np.empty((n, 32), np.uint8) if flags & SHA256 else None
-        md5 = np.empty((n, 16), np.uint8) if flags & MD5 else None
-        trimmed = np.empty(n, np.uint64)
-        rc = self._L.b200h_hash_batch_host(self._h, bp, _np_ptr(off), _np_ptr(ln), n, flags, _np_ptr(sha),
-                                           _np_ptr(md5), _np_ptr(trimmed))
+        sha = np.empty((n, 32), np.uint8) if (flags & SHA256 and not out_sha) else None
+        md5 = np.empty((n, 16), np.uint8) if (flags & MD5 and not out_md5) else None
+        trimmed = None if out_trimmed else np.empty(n, np.uint64)
+        rc = self._L.b200h_hash_batch_host(self._h, bp, _np_ptr(off), _np_ptr(ln), n, flags,
+                                           ctypes.c_void_p(out_sha) if out_sha else _np_ptr(sha),
+                                           ctypes.c_void_p(out_md5) if out_md5 else _np_ptr(md5),
+                                           ctypes.c_void_p(out_trimmed) if out_trimmed else _np_ptr(trimmed))
         self._check(rc, "b200h_hash_batch_host")
         del keep
         return sha, md5, trimmed
@@ -245,9 +268,17 @@ class Context:
 
     # -- batch over device memory (raw pointers: torch tensors' data_ptr())
     def hash_batch_device(self, d_base: int, d_offsets: int, d_lengths: int, n: int, flags: int, d_sha: int, d_md5: int,
-                          d_trimmed: int = 0, stream: int = 0):
-        rc = self._L.b200h_hash_batch_device(self._h, d_base or None, d_offsets, d_lengths, n, flags, d_sha or None,
-                                             d_md5 or None, d_trimmed or None, stream or None)
+                          d_trimmed: int = 0, stream: int = 0, h_lengths: np.ndarray | None = None):
+        """h_lengths: the same lengths as a host uint64 array -- the library then routes outliers without reading
+        anything back and the call only enqueues (b200h_hash_batch_device_hl); so does ``flags | NO_OUTLIERS``."""
+        if h_lengths is not None:
+            hl = np.ascontiguousarray(h_lengths, dtype=np.uint64)
+            assert hl.size == n
+            rc = self._L.b200h_hash_batch_device_hl(self._h, d_base or None, d_offsets, d_lengths, _np_ptr(hl), n, flags,
+                                                    d_sha or None, d_md5 or None, d_trimmed or None, stream or None)
+        else:
+            rc = self._L.b200h_hash_batch_device(self._h, d_base or None, d_offsets, d_lengths, n, flags, d_sha or None,
+                                                 d_md5 or None, d_trimmed or None, stream or None)
         self._check(rc, "b200h_hash_batch_device")
 
     def hash_fixed_parts(self, data, part_len: int, flags: int = SHA256 | MD5, want_etag: bool = False):

@@ -52,6 +52,16 @@ except Exception:
         function_call_id: str = ""
 
 
+try:  # pragma: no cover
+    from modal_proto.api_pb2 import MapStartOrContinueItem  # type: ignore
+except Exception:
+
+    @dataclasses.dataclass
+    class MapStartOrContinueItem:  # type: ignore[no-redef]  (api.proto:2543-2546)
+        input: FunctionPutInputsItem | None = None
+        attempt_token: str | None = None
+
+
 # enum ObjectCreationType, modal_proto/api.proto:207-214
 OBJECT_CREATION_TYPE_UNSPECIFIED = 0
 OBJECT_CREATION_TYPE_CREATE_IF_MISSING = 1

@@ -13,6 +13,7 @@ from typing import Sequence
 import numpy as np
 
 from . import _lib
+from ._backend import get_context
 from ._lib import MD5, SHA256, TRIM_ZEROS, Context, default_context
 
 
@@ -48,7 +49,7 @@ class DigestTable:
         keys = self.sha256 if self.sha256 is not None else self.md5
         if keys is None:
             raise ValueError("the table holds no digests")
-        return (ctx or default_context()).dedupe(keys)
+        return (ctx or get_context()).dedupe(keys)
 
     def packed(self) -> np.ndarray:
         """uint8[n,48]: sha256 || md5 per row -- the table the ranks all-gather."""
@@ -65,7 +66,7 @@ def hash_table_host(base, offsets, lengths, *, sha256: bool = True, md5: bool = 
                     ctx: Context | None = None) -> DigestTable:
     """Hash messages ``base[offsets[i] : offsets[i]+lengths[i]]`` that live in host memory
     (page-locked memory from ``Context.host_alloc`` is DMA'd directly; anything else is staged)."""
-    ctx = ctx or default_context()
+    ctx = ctx or get_context()
     flags = (SHA256 if sha256 else 0) | (MD5 if md5 else 0) | (TRIM_ZEROS if trim_zeros else 0)
     s, m, t = ctx.hash_batch_host(base, offsets, lengths, flags)
     return DigestTable(s, m, t)
@@ -73,7 +74,7 @@ def hash_table_host(base, offsets, lengths, *, sha256: bool = True, md5: bool = 
 
 def hash_table_buffers(bufs: Sequence, *, sha256: bool = True, md5: bool = True, ctx: Context | None = None) -> DigestTable:
     """Hash many separate bytes-like objects (e.g. serialized map inputs) in one GPU batch."""
-    ctx = ctx or default_context()
+    ctx = ctx or get_context()
     flags = (SHA256 if sha256 else 0) | (MD5 if md5 else 0)
     s, m, t = ctx.hash_buffers(bufs, flags)
     return DigestTable(s, m, t)
@@ -86,12 +87,14 @@ def hash_table_tensors(tensors: Sequence, *, sha256: bool = True, md5: bool = Tr
     tensors in HBM: nothing is pickled or copied before hashing."""
     import torch
 
-    ctx = ctx or default_context()
+    ctx = ctx or get_context()
     n = len(tensors)
     dev = tensors[0].device if n else torch.device("cuda", ctx.device)
     for t in tensors:
         if not (t.is_cuda and t.is_contiguous() and t.device == dev):
             raise ValueError("hash_table_tensors needs contiguous CUDA tensors on one device")
+    if n and dev.index is not None and getattr(ctx, "device", dev.index) not in (dev.index, -1):
+        raise ValueError(f"tensors live on cuda:{dev.index} but the context is bound to cuda:{ctx.device}")
     addr = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64)
     size = torch.tensor([t.numel() * t.element_size() for t in tensors], dtype=torch.int64)
     d_addr, d_size = addr.to(dev, non_blocking=False), size.to(dev, non_blocking=False)
@@ -100,8 +103,10 @@ def hash_table_tensors(tensors: Sequence, *, sha256: bool = True, md5: bool = Tr
     flags = (SHA256 if sha256 else 0) | (MD5 if md5 else 0)
     stream = torch.cuda.current_stream(dev)
     # absolute device addresses as offsets from a NULL base
+    # the sizes are known here, so the library routes outliers on the host: the call only enqueues
     ctx.hash_batch_device(0, d_addr.data_ptr(), d_size.data_ptr(), n, flags, d_sha.data_ptr() if sha256 else 0,
-                          d_md5.data_ptr() if md5 else 0, 0, stream.cuda_stream)
+                          d_md5.data_ptr() if md5 else 0, 0, stream.cuda_stream,
+                          h_lengths=size.numpy().astype(np.uint64))
     # the library launched on this stream (or, for the legacy default stream, on its own): make the result
     # visible to the caller's stream before the offset tensors can be freed
     if stream.cuda_stream == 0:

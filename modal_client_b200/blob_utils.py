@@ -317,9 +317,13 @@ async def _blob_upload(
     progress_report_cb: Callable | None = None,
     byte_budget: _ByteBudget | None = None,
 ) -> tuple[str, bool, int]:
+    """BlobCreate with the precomputed digests, then a single PUT or a multipart upload (reference :271-335).
+    The map pump calls this once per blobified input, 10^5 times per map: a ``bytes`` payload is not wrapped in a
+    reader (nor is its aiohttp payload object built) before a PUT actually needs one."""
     if isinstance(data, bytes):
-        data = BytesIO(data)
-    content_length = get_content_length(data)
+        reader, content_length = None, len(data)
+    else:
+        reader, content_length = data, get_content_length(data)
     resp = await stub.BlobCreate(
         BlobCreateRequest(
             content_md5=upload_hashes.md5_base64,
@@ -328,10 +332,12 @@ async def _blob_upload(
         )
     )
     if resp.WhichOneof("upload_types_oneof") == "multiparts":
+        if reader is None:
+            reader = BytesIO(data)
 
         async def send_multipart(part):
             return await perform_multipart_upload(
-                data,
+                reader,
                 content_length=content_length,
                 max_part_size=part.part_length,
                 part_urls=part.upload_urls,
@@ -343,15 +349,20 @@ async def _blob_upload(
 
         result = await _blob_upload_with_fallback(resp.multiparts.items, resp.blob_ids, send_multipart, content_length)
     else:
-        from .bytes_io_segment_payload import BytesIOSegmentPayload
-
-        # the whole-blob MD5 is already in upload_hashes: hand it to the payload instead of re-hashing
-        payload = BytesIOSegmentPayload(
-            data, segment_start=0, segment_length=content_length, progress_report_cb=progress_report_cb,
-            md5_digest=bytes.fromhex(upload_hashes.md5_hex()) if _is_real_md5(upload_hashes) else None,
-        )
+        payload = None
 
         async def send_single(url):
+            nonlocal payload
+            if payload is None:
+                from .bytes_io_segment_payload import BytesIOSegmentPayload
+
+                # the whole-blob MD5 is already in upload_hashes: hand it to the payload instead of re-hashing
+                raw = getattr(upload_hashes, "md5_raw", None)
+                if raw is None and _is_real_md5(upload_hashes):
+                    raw = bytes.fromhex(upload_hashes.md5_hex())
+                payload = BytesIOSegmentPayload(
+                    reader if reader is not None else BytesIO(data), segment_start=0, segment_length=content_length,
+                    progress_report_cb=progress_report_cb, md5_digest=raw)
             return await _upload_to_s3_url(url, payload, content_md5_b64=upload_hashes.md5_base64)
 
         result = await _blob_upload_with_fallback(resp.upload_urls.items, resp.blob_ids, send_single, content_length)

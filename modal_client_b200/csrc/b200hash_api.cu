@@ -12,8 +12,12 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -36,6 +40,45 @@ static const uint32_t kMd5Iv[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x1032
 namespace {
 
 thread_local std::string g_create_error;
+
+// NVTX range around every C-ABI entry point (visible in nsys / ncu --nvtx; a no-op without an injected tool)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define B200H_RANGE(name) NvtxRange nvtx_range__(name)
+
+// One caller's small b200h_hash_batch_host request while it waits to be merged with its neighbours'.
+struct CombineReq {
+    const uint8_t* base;
+    const uint64_t* off;
+    const uint64_t* len;
+    uint64_t n;
+    uint32_t flags;
+    uint8_t* sha;
+    uint8_t* md5;
+    uint64_t* trim;
+    int rc = 0;
+    bool done = false;
+};
+
+// Combining queue for concurrent small requests (the reference's ThreadPool / to_thread callers each hash ONE
+// file, block or payload per call: py/modal/volume.py:1209-1216, blob_utils.py:622-645).  The first caller in
+// becomes the leader; while it waits for the context (the GPU is busy with the previous group) the others join
+// its group; the leader then issues ONE batch for all of them and hands every caller its own digests.
+struct Combiner {
+    std::mutex m;
+    std::condition_variable cv_done, cv_more;
+    std::vector<CombineReq*> pending[2];  // [B200H_TRIM_ZEROS?]: trimming changes what a message means, never mixed
+    bool leader[2] = {false, false};
+    bool recent_multi = false;  // the last group had company: worth waiting a moment for the next one to fill
+    uint64_t groups = 0, requests = 0;
+};
+constexpr uint64_t kCombineMaxN = 1024;     // requests with more messages fill the GPU on their own
+constexpr size_t kCombineFull = 64;          // stop waiting for company at this many callers
+constexpr int kCombineWaitUs = 200;
 
 struct DevBuf {
     void* p = nullptr;
@@ -71,6 +114,18 @@ struct b200h_ctx {
     uint32_t chain_cap = 592;
     int* h_plan = nullptr;        // pinned: the planner's control block {avail, head, tail, outliers} of the last batch
     uint32_t last_outliers = 0;
+    bool verify_plan = false;     // B200H_VERIFY_PLAN=1: cross-check the host-side outlier count against the device's
+    uint64_t plan_syncs = 0;      // enqueues that had to read the outlier count back (stream synchronisation)
+    Combiner combiner;
+    bool combine_enabled = true;  // B200H_COMBINE=0 turns the combining queue off
+    struct StreamBuf {            // resources of a b200h_stream, pooled per context (allocation costs ~1 ms)
+        uint8_t* h = nullptr;     // pinned host accumulation buffer
+        uint8_t* d = nullptr;     // device block: states | meta | out | plan scratch | ring | data
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+    };
+    std::vector<StreamBuf> stream_pool;
+    size_t stream_cap = size_t(4) << 20;  // bytes absorbed per kernel launch (B200H_STREAM_BUF)
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};    // H2D of a wave slot finished
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // kernels reading a wave slot finished
     cudaEvent_t ev_pin[2] = {nullptr, nullptr};       // H2D out of a pinned slot finished
@@ -83,7 +138,7 @@ struct b200h_ctx {
     uint8_t* dwave[2] = {nullptr, nullptr};
     size_t dwave_cap = 0;  // per slot
     size_t dwave_want = 0;
-    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small, d_states, d_dedupe, d_keys;
+    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small, d_states, d_dedupe, d_keys, d_trimctl;
     uint64_t* h_meta = nullptr;  // pinned: offsets then lengths
     size_t h_meta_cap = 0;       // in uint64 elements
     uint64_t launches = 0;
@@ -98,17 +153,23 @@ struct b200h_ctx {
 struct b200h_stream {
     b200h_ctx* ctx = nullptr;
     uint32_t flags = 0;
-    uint8_t* hbuf = nullptr;  // host accumulation buffer (cap bytes, multiple of 64)
+    b200h_ctx::StreamBuf res;
+    uint8_t* hbuf = nullptr;  // = res.h: pinned host accumulation buffer (cap bytes, multiple of 64)
     size_t cap = 0;
     size_t fill = 0;
+    bool h2d_pending = false;      // res.ev marks the end of the last copy out of hbuf
     uint8_t* d_buf = nullptr;      // device copy of hbuf
     ChainState* d_state = nullptr; // [0] running state, [1] scratch copy for digest()
     uint64_t* d_meta = nullptr;    // off, len
     uint8_t* d_out = nullptr;      // 32 + 16
+    uint32_t* d_plan = nullptr;    // this stream's own planner scratch + ring: its launches never wait for other batches
+    uint32_t* d_ring = nullptr;
     uint64_t total = 0;
 };
 
 namespace {
+
+void stream_res_destroy(b200h_ctx::StreamBuf& r);  // defined with the streaming entry points
 
 int fail(b200h_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -184,19 +245,28 @@ int prof_end(b200h_ctx* ctx, cudaStream_t st, cudaEvent_t a, cudaEvent_t b) {
     return 0;
 }
 
+constexpr uint32_t kFlagNoFinal = 0x80000000u;  // internal: continuation segment (no padding, state written back)
+
 // Enqueue trim -> plan -> lane_hash for n device-resident messages on `st`.  ctx->mu must be held.
+// h_len (may be NULL) = the same lengths on the host.  With them the outlier routing is decided here without reading
+// anything back, so the call only enqueues; without them (and without B200H_NO_OUTLIERS) the planner's count is
+// read back after the ~12 us plan kernels, which synchronises `st` once.
 int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* d_off, const uint64_t* d_len,
                          uint64_t n, uint32_t flags, uint8_t* d_sha, uint8_t* d_md5, uint64_t* d_trim_out,
-                         ChainState* d_state, cudaStream_t st) {
+                         ChainState* d_state, cudaStream_t st, const uint64_t* h_len = nullptr,
+                         uint32_t* own_scratch = nullptr, uint32_t* own_ring = nullptr) {
     if (n == 0) return 0;
     if (n > 0xffffffffull) return fail(ctx, B200H_E_INVALID, "batch larger than 2^32-1 messages");
     uint32_t kflags = 0;
     if (flags & B200H_SHA256) kflags |= F_SHA256;
     if (flags & B200H_MD5) kflags |= F_MD5;
-    if (flags & 0x80000000u) kflags |= F_NO_FINAL;  // internal: continuation segment
+    if (flags & kFlagNoFinal) kflags |= F_NO_FINAL;
     if (!(kflags & (F_SHA256 | F_MD5))) return fail(ctx, B200H_E_INVALID, "flags select neither SHA256 nor MD5");
 
-    if (ctx->scratch_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
+    // own_scratch / own_ring: planner scratch and queue ring private to the caller (a b200h_stream): the batch then
+    // shares nothing with other batches of the context and runs concurrently with them on its own CUDA stream.
+    const bool shared_scratch = own_scratch == nullptr;
+    if (shared_scratch && ctx->scratch_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
     const uint64_t* len_used = d_len;
     if (flags & B200H_TRIM_ZEROS) {
         uint64_t* tbuf = d_trim_out;
@@ -204,17 +274,22 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
             if (int rc = ensure_dev(ctx, ctx->d_trim, n * sizeof(uint64_t))) return rc;
             tbuf = (uint64_t*)ctx->d_trim.p;
         }
-        ctx->launches += launch_trim(d_base, d_off, d_len, n, tbuf, st);
+        if (int rc = ensure_dev(ctx, ctx->d_trimctl, 16 + n * sizeof(TrimWideEntry))) return rc;
+        ctx->launches += launch_trim(d_base, d_off, d_len, n, tbuf, (unsigned long long*)ctx->d_trimctl.p,
+                                     (TrimWideEntry*)((uint8_t*)ctx->d_trimctl.p + 16), st);
         len_used = tbuf;
+        h_len = nullptr;  // the lengths that matter now exist on the device only
     } else if (d_trim_out) {
         CU_TRY(ctx, cudaMemcpyAsync(d_trim_out, d_len, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     }
     // work queue (ring + control block) and chaining-state scratch for the persistent lane kernel
     if (n >= 0x7fffffffull) return fail(ctx, B200H_E_INVALID, "batch larger than 2^31-2 messages");
-    if (int rc = ensure_dev(ctx, ctx->d_order, (size_t)ring_capacity(n) * sizeof(uint32_t))) return rc;
-    if (int rc = ensure_dev(ctx, ctx->d_scratch, (kPlanScratchWords + kMaxChain) * sizeof(uint32_t))) return rc;
-    uint32_t* ring = (uint32_t*)ctx->d_order.p;
-    uint32_t* scratch = (uint32_t*)ctx->d_scratch.p;
+    if (shared_scratch) {
+        if (int rc = ensure_dev(ctx, ctx->d_order, (size_t)ring_capacity(n) * sizeof(uint32_t))) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_scratch, (kPlanScratchWords + kMaxChain) * sizeof(uint32_t))) return rc;
+    }
+    uint32_t* ring = shared_scratch ? (uint32_t*)ctx->d_order.p : own_ring;
+    uint32_t* scratch = shared_scratch ? (uint32_t*)ctx->d_scratch.p : own_scratch;
     uint32_t* chain_list = scratch + kPlanScratchWords;
     int* qctl = plan_qctl(scratch);
     ChainState* states = d_state;
@@ -223,20 +298,36 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
         states = (ChainState*)ctx->d_states.p;
     }
     const bool resume = d_state != nullptr;
-    ctx->launches += launch_plan(len_used, n, ring, chain_list, scratch, /*fresh=*/!resume,
-                                 ctx->chain_enabled ? ctx->chain_cap : 0u, st);
+    const bool chain_on = ctx->chain_enabled && !(flags & B200H_NO_OUTLIERS);
+    const uint32_t max_chain = chain_on ? ctx->chain_cap : 0u;
+    ctx->launches += launch_plan(len_used, n, ring, chain_list, scratch, /*fresh=*/!resume, max_chain, st);
     // How many outliers did the planner pick?  The count is read back (16 bytes, one stream synchronisation after
     // the ~12 us plan kernels) because a chain kernel launched "just in case" is not free: its CTAs ask for half an
     // SM's shared memory and, idle or not, skew where the lane kernel's CTAs land (1 024 x 8 MiB: 260 -> 937 ms,
     // 2 048 x 4 MiB: 159 -> 280 ms measured with a speculative launch before / after the lane kernel).
+    // So: lengths known on the host -> the same selection is computed here (plan_outliers_host); otherwise read back.
     uint32_t n_chain = 0;
-    if (ctx->chain_enabled) {
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, qctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaStreamSynchronize(st));
-        n_chain = (uint32_t)ctx->h_plan[3];
+    if (chain_on) {
+        const bool mirrored = h_len != nullptr;
+        if (mirrored) n_chain = plan_outliers_host(h_len, n, max_chain);
+        if (!mirrored || ctx->verify_plan) {
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, qctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            ctx->plan_syncs += 1;
+            if (mirrored && n_chain != (uint32_t)ctx->h_plan[3]) {
+                char b[128];
+                snprintf(b, sizeof b, "outlier plan mismatch: host %u, device %d", n_chain, ctx->h_plan[3]);
+                return fail(ctx, B200H_E_STATE, b);
+            }
+            n_chain = (uint32_t)ctx->h_plan[3];
+        }
     }
     ctx->last_outliers = n_chain;
-    if (n_chain) {
+    if (n_chain && !shared_scratch) {
+        // a private single-message batch: the chain kernel IS the batch, no side stream needed
+        ctx->launches += launch_chain_hash(d_base, d_off, len_used, chain_list, qctl, kflags, d_sha, d_md5, states,
+                                           resume, n_chain, st);
+    } else if (n_chain) {
         // the outliers set the makespan: their CTAs go first (high-priority stream), one per SM
         CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_chain, ctx->ev_fork, 0));
@@ -248,10 +339,12 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     if (int rc = prof_begin(ctx, st, &pa, &pb)) return rc;
     ctx->launches += launch_lane_hash(d_base, d_off, len_used, ring, qctl, n, kflags, d_sha, d_md5, states, st);
     if (int rc = prof_end(ctx, st, pa, pb)) return rc;
-    if (n_chain) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (n_chain && shared_scratch) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU_TRY(ctx, cudaGetLastError());
-    CU_TRY(ctx, cudaEventRecord(ctx->ev_scratch, st));
-    ctx->scratch_used = true;
+    if (shared_scratch) {
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_scratch, st));
+        ctx->scratch_used = true;
+    }
     return 0;
 }
 
@@ -385,11 +478,23 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
     CU_TRY(ctx, cudaSetDevice(ctx->device));
 
     // Page-locked source?  Then DMA straight from the caller's memory, no staging copy.
+    // (Only when the messages cover most of the span they sit in: a wave DMAs its whole [min offset, max end) span,
+    // so a sparse selection -- one rank's interleaved shard of a shared buffer -- would copy the gaps too; those
+    // are gathered through the staging ring like pageable memory.)
     bool direct = false;
     if (base && !paths) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, base) == cudaSuccess) direct = (at.type == cudaMemoryTypeHost);
         else cudaGetLastError();
+        if (direct) {
+            uint64_t lo = ~0ull, hi = 0, payload = 0;
+            for (uint64_t i = 0; i < n; ++i) {
+                lo = std::min(lo, off[i]);
+                hi = std::max(hi, off[i] + len[i]);
+                payload += len[i];
+            }
+            if (hi - lo > payload + payload / 4 + (uint64_t(16) << 20)) direct = false;
+        }
     }
 
     if (int rc = ensure_meta(ctx, 2 * n)) return rc;
@@ -528,10 +633,11 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
             }
             const uint64_t meta[2] = {0, w.bytes};
             CU_TRY(ctx, cudaMemcpyAsync(d_segmeta, meta, sizeof meta, cudaMemcpyHostToDevice, ctx->s_comp));
-            const uint32_t f = (flags & 3u) | (w.seg == 2 ? 0u : 0x80000000u);
+            const uint32_t f = (flags & (3u | B200H_NO_OUTLIERS)) | (w.seg == 2 ? 0u : kFlagNoFinal);
+            const uint64_t seg_bytes = w.bytes;
             if (int rc = enqueue_device_batch(ctx, ctx->dwave[slot], d_segmeta, d_segmeta + 1, 1, f,
                                               d_sha ? d_sha + 32 * w.i0 : nullptr, d_md5 ? d_md5 + 16 * w.i0 : nullptr,
-                                              nullptr, d_segstate, ctx->s_comp))
+                                              nullptr, d_segstate, ctx->s_comp, &seg_bytes))
                 return rc;
             if (w.seg == 2)
                 CU_TRY(ctx, cudaMemcpyAsync(d_trim + w.i0, d_len + w.i0, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->s_comp));
@@ -540,7 +646,7 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
         }
         if (int rc = enqueue_device_batch(ctx, ctx->dwave[slot], d_off + w.i0, d_len + w.i0, cnt, flags,
                                           d_sha ? d_sha + 32 * w.i0 : nullptr, d_md5 ? d_md5 + 16 * w.i0 : nullptr,
-                                          d_trim + w.i0, nullptr, ctx->s_comp))
+                                          d_trim + w.i0, nullptr, ctx->s_comp, len + w.i0))
             return rc;
         CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[slot], ctx->s_comp));
     }
@@ -554,15 +660,90 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
         d_etag = (uint8_t*)ctx->d_small.p + 32;
         CU_TRY(ctx, cudaMemcpyAsync(d_meta, meta, sizeof meta, cudaMemcpyHostToDevice, ctx->s_comp));
         if (int rc = enqueue_device_batch(ctx, d_md5, d_meta, d_meta + 1, 1, B200H_MD5, nullptr, d_etag, nullptr,
-                                          nullptr, ctx->s_comp))
+                                          nullptr, ctx->s_comp, &meta[1]))
             return rc;
     }
+    // The output arrays may live in host OR device memory (cudaMemcpyDefault): a caller that goes on to all-gather
+    // the table over NCCL passes device buffers and the digests never visit the host.
+    if (sha_out && d_sha) CU_TRY(ctx, cudaMemcpyAsync(sha_out, d_sha, n * 32, cudaMemcpyDefault, ctx->s_comp));
+    if (md5_out && d_md5) CU_TRY(ctx, cudaMemcpyAsync(md5_out, d_md5, n * 16, cudaMemcpyDefault, ctx->s_comp));
+    if (trim_out) CU_TRY(ctx, cudaMemcpyAsync(trim_out, d_trim, n * sizeof(uint64_t), cudaMemcpyDefault, ctx->s_comp));
+    if (etag_out) CU_TRY(ctx, cudaMemcpyAsync(etag_out, d_etag, 16, cudaMemcpyDefault, ctx->s_comp));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->s_comp));
-    if (sha_out && d_sha) CU_TRY(ctx, cudaMemcpy(sha_out, d_sha, n * 32, cudaMemcpyDeviceToHost));
-    if (md5_out && d_md5) CU_TRY(ctx, cudaMemcpy(md5_out, d_md5, n * 16, cudaMemcpyDeviceToHost));
-    if (trim_out) CU_TRY(ctx, cudaMemcpy(trim_out, d_trim, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    if (etag_out) CU_TRY(ctx, cudaMemcpy(etag_out, d_etag, 16, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+constexpr uint32_t kPublicFlags = 7u | B200H_NO_OUTLIERS;
+
+// A small request from one of possibly many concurrent callers: merge it with whatever else arrives while the context
+// is busy, run ONE batch, hand every caller its rows.  (See Combiner.)
+int combined_hash_batch_host(b200h_ctx* ctx, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n,
+                             uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, uint64_t* trim_out) {
+    Combiner& cb = ctx->combiner;
+    CombineReq r{base, off, len, n, flags, sha_out, md5_out, trim_out};
+    const int k = (flags & B200H_TRIM_ZEROS) ? 1 : 0;
+    std::unique_lock<std::mutex> cl(cb.m);
+    cb.pending[k].push_back(&r);
+    if (cb.leader[k]) {  // somebody is already collecting this group: ride along
+        cb.cv_more.notify_one();
+        cb.cv_done.wait(cl, [&] { return r.done; });
+        return r.rc;
+    }
+    cb.leader[k] = true;
+    if (cb.recent_multi && cb.pending[k].size() < kCombineFull)  // concurrent callers were seen a moment ago
+        cb.cv_more.wait_for(cl, std::chrono::microseconds(kCombineWaitUs), [&] { return cb.pending[k].size() >= kCombineFull; });
+    cl.unlock();
+    std::unique_lock<std::mutex> gl(ctx->mu);  // while the previous group occupies the GPU, callers keep joining this one
+    cl.lock();
+    std::vector<CombineReq*> grp;
+    grp.swap(cb.pending[k]);
+    cb.leader[k] = false;
+    cb.recent_multi = grp.size() > 1;
+    cb.groups += 1;
+    cb.requests += grp.size();
+    cl.unlock();
+
+    int rc = 0;
+    if (grp.size() == 1) {
+        rc = hash_batch_host_impl(ctx, base, off, len, n, flags, sha_out, md5_out, trim_out, nullptr);
+        gl.unlock();
+    } else {
+        uint64_t total = 0;
+        uint32_t uflags = 0;
+        for (CombineReq* q : grp) {
+            total += q->n;
+            uflags |= q->flags;
+        }
+        std::vector<uint64_t> aoff(total), alen(total), ttrim(total);
+        std::vector<uint8_t> tsha((uflags & B200H_SHA256) ? total * 32 : 0), tmd5((uflags & B200H_MD5) ? total * 16 : 0);
+        uint64_t at = 0;
+        for (CombineReq* q : grp)
+            for (uint64_t i = 0; i < q->n; ++i, ++at) {
+                aoff[at] = (uint64_t)(uintptr_t)q->base + q->off[i];  // absolute addresses, base = NULL
+                alen[at] = q->len[i];
+            }
+        rc = total ? hash_batch_host_impl(ctx, nullptr, aoff.data(), alen.data(), total, uflags,
+                                          tsha.empty() ? nullptr : tsha.data(), tmd5.empty() ? nullptr : tmd5.data(),
+                                          ttrim.data(), nullptr)
+                   : 0;
+        gl.unlock();
+        at = 0;
+        for (CombineReq* q : grp) {
+            if (!rc) {
+                if (q->sha && (q->flags & B200H_SHA256)) memcpy(q->sha, tsha.data() + at * 32, q->n * 32);
+                if (q->md5 && (q->flags & B200H_MD5)) memcpy(q->md5, tmd5.data() + at * 16, q->n * 16);
+                if (q->trim) memcpy(q->trim, ttrim.data() + at, q->n * sizeof(uint64_t));
+            }
+            at += q->n;
+        }
+    }
+    cl.lock();
+    for (CombineReq* q : grp) {
+        q->rc = rc;
+        q->done = true;
+    }
+    cb.cv_done.notify_all();
+    return rc;
 }
 
 }  // namespace
@@ -653,6 +834,12 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
     if (const char* e = getenv("B200H_PACK_THREADS")) ctx->pack_threads = std::max(1, atoi(e));
     ctx->io_threads = (int)std::min(16u, std::max(1u, hc));  // measured: 16 > 32 > 64 > 128 (kernel-side contention)
     if (const char* e = getenv("B200H_IO_THREADS")) ctx->io_threads = std::max(1, atoi(e));
+    if (const char* e = getenv("B200H_VERIFY_PLAN")) ctx->verify_plan = atoi(e) != 0;
+    if (const char* e = getenv("B200H_COMBINE")) ctx->combine_enabled = atoi(e) != 0;
+    if (const char* e = getenv("B200H_STREAM_BUF")) {
+        const long long v = atoll(e);
+        if (v >= 65536) ctx->stream_cap = (size_t)v & ~size_t(63);
+    }
 #undef CU_INIT
     *out = ctx;
     return 0;
@@ -667,8 +854,10 @@ void b200h_destroy(b200h_ctx* ctx) {
         cudaEventDestroy(pr.second);
     }
     for (DevBuf* b : {&ctx->d_off, &ctx->d_len, &ctx->d_order, &ctx->d_trim, &ctx->d_sha, &ctx->d_md5, &ctx->d_scratch,
-                      &ctx->d_small, &ctx->d_states, &ctx->d_dedupe, &ctx->d_keys})
+                      &ctx->d_small, &ctx->d_states, &ctx->d_dedupe, &ctx->d_keys, &ctx->d_trimctl})
         if (b->p) cudaFree(b->p);
+    for (auto& r : ctx->stream_pool) stream_res_destroy(r);
+    ctx->stream_pool.clear();
     for (int s = 0; s < 2; ++s) {
         if (ctx->dwave[s]) cudaFree(ctx->dwave[s]);
         if (ctx->pin[s]) cudaFreeHost(ctx->pin[s]);
@@ -711,30 +900,43 @@ int b200h_hash_batch_host(b200h_ctx* ctx, const uint8_t* base, const uint64_t* o
                           uint64_t n, uint32_t flags, uint8_t* sha256_out, uint8_t* md5_out,
                           uint64_t* trimmed_len_out) {
     if (!ctx) return B200H_E_INVALID;
+    B200H_RANGE("b200h_hash_batch_host");
+    if (n && n <= kCombineMaxN && ctx->combine_enabled && offsets && lengths && (flags & (B200H_SHA256 | B200H_MD5)))
+        return combined_hash_batch_host(ctx, base, offsets, lengths, n, flags & kPublicFlags, sha256_out, md5_out,
+                                        trimmed_len_out);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    return hash_batch_host_impl(ctx, base, offsets, lengths, n, flags & 7u, sha256_out, md5_out, trimmed_len_out,
-                                nullptr);
+    return hash_batch_host_impl(ctx, base, offsets, lengths, n, flags & kPublicFlags, sha256_out, md5_out,
+                                trimmed_len_out, nullptr);
 }
 
-int b200h_hash_batch_device(b200h_ctx* ctx, const void* d_base, const uint64_t* d_offsets, const uint64_t* d_lengths,
-                            uint64_t n, uint32_t flags, void* d_sha256, void* d_md5, uint64_t* d_trimmed_len,
-                            void* cuda_stream) {
+int b200h_hash_batch_device_hl(b200h_ctx* ctx, const void* d_base, const uint64_t* d_offsets, const uint64_t* d_lengths,
+                               const uint64_t* h_lengths, uint64_t n, uint32_t flags, void* d_sha256, void* d_md5,
+                               uint64_t* d_trimmed_len, void* cuda_stream) {
     if (!ctx) return B200H_E_INVALID;
+    B200H_RANGE("b200h_hash_batch_device");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (n && (!d_offsets || !d_lengths)) return fail(ctx, B200H_E_INVALID, "offsets/lengths must not be NULL");
     if (((uintptr_t)d_sha256 | (uintptr_t)d_md5) & 15u)
         return fail(ctx, B200H_E_INVALID, "digest outputs must be 16-byte aligned");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->s_comp;
-    return enqueue_device_batch(ctx, (const uint8_t*)d_base, d_offsets, d_lengths, n, flags & 7u,
+    return enqueue_device_batch(ctx, (const uint8_t*)d_base, d_offsets, d_lengths, n, flags & kPublicFlags,
                                 (flags & B200H_SHA256) ? (uint8_t*)d_sha256 : nullptr,
-                                (flags & B200H_MD5) ? (uint8_t*)d_md5 : nullptr, d_trimmed_len, nullptr, st);
+                                (flags & B200H_MD5) ? (uint8_t*)d_md5 : nullptr, d_trimmed_len, nullptr, st, h_lengths);
+}
+
+int b200h_hash_batch_device(b200h_ctx* ctx, const void* d_base, const uint64_t* d_offsets, const uint64_t* d_lengths,
+                            uint64_t n, uint32_t flags, void* d_sha256, void* d_md5, uint64_t* d_trimmed_len,
+                            void* cuda_stream) {
+    return b200h_hash_batch_device_hl(ctx, d_base, d_offsets, d_lengths, nullptr, n, flags, d_sha256, d_md5,
+                                      d_trimmed_len, cuda_stream);
 }
 
 int b200h_hash_fixed_parts(b200h_ctx* ctx, const uint8_t* base, uint64_t len, uint64_t part_len, uint32_t flags,
                            uint8_t* sha256_out, uint8_t* md5_out, uint64_t* trimmed_len_out, uint8_t etag_md5_out[16],
                            uint64_t* nparts_out) {
     if (!ctx) return B200H_E_INVALID;
+    B200H_RANGE("b200h_hash_fixed_parts");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (part_len == 0) return fail(ctx, B200H_E_INVALID, "part_len must be > 0");
     const uint64_t nparts = (len + part_len - 1) / part_len;
@@ -753,7 +955,7 @@ int b200h_hash_fixed_parts(b200h_ctx* ctx, const uint8_t* base, uint64_t len, ui
         off[i] = i * part_len;
         ln[i] = std::min(part_len, len - off[i]);
     }
-    return hash_batch_host_impl(ctx, base, off.data(), ln.data(), nparts, flags & 7u, sha256_out, md5_out,
+    return hash_batch_host_impl(ctx, base, off.data(), ln.data(), nparts, flags & kPublicFlags, sha256_out, md5_out,
                                 trimmed_len_out, etag_md5_out);
 }
 
@@ -761,6 +963,7 @@ int b200h_hash_fixed_parts(b200h_ctx* ctx, const uint8_t* base, uint64_t len, ui
 
 int b200h_stat_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, uint64_t* sizes_out, uint32_t* modes_out) {
     if (!ctx) return B200H_E_INVALID;
+    B200H_RANGE("b200h_stat_files");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (n && (!paths || !sizes_out)) return fail(ctx, B200H_E_INVALID, "paths/sizes_out must not be NULL");
     std::atomic<int> err{0};
@@ -792,6 +995,7 @@ int b200h_stat_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, uint6
 int b200h_hash_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, const uint64_t* sizes, uint64_t part_len,
                      uint32_t flags, uint8_t* sha256_out, uint8_t* md5_out, uint64_t* trimmed_len_out) {
     if (!ctx) return B200H_E_INVALID;
+    B200H_RANGE("b200h_hash_files");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (n && (!paths || !sizes)) return fail(ctx, B200H_E_INVALID, "paths/sizes must not be NULL");
     // message list: one per file (part_len == 0) or one per part_len-sized part, file-major
@@ -810,42 +1014,111 @@ int b200h_hash_files(b200h_ctx* ctx, const char* const* paths, uint64_t n, const
         }
     }
     if (off.empty()) return 0;
-    return hash_batch_host_impl(ctx, nullptr, off.data(), len.data(), off.size(), flags & 7u, sha256_out, md5_out,
-                                trimmed_len_out, nullptr, paths, file_of.data());
+    return hash_batch_host_impl(ctx, nullptr, off.data(), len.data(), off.size(), flags & kPublicFlags, sha256_out,
+                                md5_out, trimmed_len_out, nullptr, paths, file_of.data());
 }
 
 // ------------------------------------------------------------------------------------------ streaming
+// A b200h_stream owns a CUDA stream, a pinned accumulation buffer and a device block that holds everything its
+// launches touch (chaining state, planner scratch, queue ring, data), so several streams of one context -- the
+// reference hashes files from ThreadPool / to_thread workers, one hashlib object each -- advance concurrently on the
+// GPU, one chain per stream.  update() only copies into the pinned buffer; every `cap` bytes one absorb is enqueued
+// (H2D + plan + chain kernel) and update() returns without waiting for it: the next absorb's bytes are gathered
+// while the GPU works on this one.  The host knows every length, so nothing is read back.
 
+extern "C++" {
+namespace {
 
-static int stream_write_iv(b200h_stream* s) {
+constexpr size_t kStreamStateBytes = 2 * sizeof(ChainState);  // [0] running, [1] scratch copy for digest()
+constexpr size_t kStreamMetaOff = kStreamStateBytes;          // 2 x u64
+constexpr size_t kStreamOutOff = kStreamMetaOff + 64;         // 32 + 16
+constexpr size_t kStreamPlanOff = kStreamOutOff + 64;         // planner scratch + chain list
+constexpr size_t kStreamPlanBytes = (kPlanScratchWords + kMaxChain) * sizeof(uint32_t);
+constexpr size_t kStreamRingOff = (kStreamPlanOff + kStreamPlanBytes + 127) & ~size_t(127);
+constexpr size_t kStreamRingBytes = 32 * sizeof(uint32_t);    // ring_capacity(1)
+constexpr size_t kStreamDataOff = (kStreamRingOff + kStreamRingBytes + 255) & ~size_t(255);
+
+int stream_res_acquire(b200h_ctx* ctx, b200h_ctx::StreamBuf* out) {
+    if (!ctx->stream_pool.empty()) {
+        *out = ctx->stream_pool.back();
+        ctx->stream_pool.pop_back();
+        return 0;
+    }
+    b200h_ctx::StreamBuf r;
+    cudaError_t e = cudaHostAlloc(&r.h, ctx->stream_cap + 128, cudaHostAllocDefault);  // + pinned {offset, length} slots and digests
+    if (e == cudaSuccess) e = cudaMalloc(&r.d, kStreamDataOff + ctx->stream_cap + 64);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (r.h) cudaFreeHost(r.h);
+        if (r.d) cudaFree(r.d);
+        if (r.st) cudaStreamDestroy(r.st);
+        if (r.ev) cudaEventDestroy(r.ev);
+        return fail(ctx, B200H_E_NOMEM, std::string("stream allocation failed: ") + cudaGetErrorString(e));
+    }
+    *out = r;
+    return 0;
+}
+
+void stream_res_destroy(b200h_ctx::StreamBuf& r) {
+    if (r.st) cudaStreamSynchronize(r.st);
+    if (r.h) cudaFreeHost(r.h);
+    if (r.d) cudaFree(r.d);
+    if (r.st) cudaStreamDestroy(r.st);
+    if (r.ev) cudaEventDestroy(r.ev);
+    cudaGetLastError();
+    r = b200h_ctx::StreamBuf();
+}
+
+int stream_write_iv(b200h_stream* s) {
     b200h_ctx* ctx = s->ctx;
     ChainState init;
     memcpy(init.sha, kShaIv, sizeof kShaIv);
     memcpy(init.md5, kMd5Iv, sizeof kMd5Iv);
     init.prior_bytes = 0;
     init.reserved = 0;
-    CU_TRY(ctx, cudaMemcpy(s->d_state, &init, sizeof init, cudaMemcpyHostToDevice));
+    // {0, cap}: offset and length of every absorb, device-resident for the life of the stream (no per-absorb copy)
+    uint64_t* h_meta = reinterpret_cast<uint64_t*>(s->hbuf + s->cap);
+    h_meta[0] = 0;
+    h_meta[1] = s->cap;
+    CU_TRY(ctx, cudaMemcpyAsync(s->d_state, &init, sizeof init, cudaMemcpyHostToDevice, s->res.st));
+    CU_TRY(ctx, cudaMemcpyAsync(s->d_meta, h_meta, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, s->res.st));
+    CU_TRY(ctx, cudaStreamSynchronize(s->res.st));  // also drains whatever the stream still had in flight
+    s->h2d_pending = false;
     s->fill = 0;
     s->total = 0;
     return 0;
 }
 
-// absorb the first `nbytes` (multiple of 64) of hbuf into the running state
-static int stream_absorb(b200h_stream* s, size_t nbytes) {
-    b200h_ctx* ctx = s->ctx;
-    if (!nbytes) return 0;
-    const uint64_t meta[2] = {0, nbytes};
-    CU_TRY(ctx, cudaMemcpyAsync(s->d_buf, s->hbuf, nbytes, cudaMemcpyHostToDevice, ctx->s_comp));
-    CU_TRY(ctx, cudaMemcpyAsync(s->d_meta, meta, sizeof meta, cudaMemcpyHostToDevice, ctx->s_comp));
-    if (int rc = enqueue_device_batch(ctx, s->d_buf, s->d_meta, s->d_meta + 1, 1, (s->flags & 3u) | 0x80000000u,
-                                      nullptr, nullptr, nullptr, s->d_state, ctx->s_comp))
-        return rc;
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_comp));
+// hbuf may be rewritten once the last copy out of it has finished (waits outside the context lock)
+int stream_wait_hbuf(b200h_stream* s) {
+    if (s->h2d_pending) {
+        CU_TRY(s->ctx, cudaEventSynchronize(s->res.ev));
+        s->h2d_pending = false;
+    }
     return 0;
 }
 
+// enqueue: absorb the first `nbytes` (multiple of 64) of hbuf into the running state.  ctx->mu must be held.
+int stream_absorb(b200h_stream* s, size_t nbytes) {
+    b200h_ctx* ctx = s->ctx;
+    if (nbytes != s->cap) return fail(ctx, B200H_E_STATE, "stream absorbs whole buffers only");
+    const uint64_t hlen = nbytes;
+    cudaStream_t st = s->res.st;
+    CU_TRY(ctx, cudaMemcpyAsync(s->d_buf, s->hbuf, nbytes, cudaMemcpyHostToDevice, st));  // pinned: truly asynchronous
+    CU_TRY(ctx, cudaEventRecord(s->res.ev, st));
+    s->h2d_pending = true;
+    return enqueue_device_batch(ctx, s->d_buf, s->d_meta, s->d_meta + 1, 1, (s->flags & 3u) | kFlagNoFinal, nullptr,
+                                nullptr, nullptr, s->d_state, st, &hlen, s->d_plan, s->d_ring);
+}
+
+}  // namespace
+}  // extern "C++"
+
 int b200h_stream_new(b200h_ctx* ctx, uint32_t flags, b200h_stream** out) {
     if (!ctx || !out) return B200H_E_INVALID;
+    B200H_RANGE("b200h_stream_new");
     std::lock_guard<std::mutex> lk(ctx->mu);
     *out = nullptr;
     if (!(flags & (B200H_SHA256 | B200H_MD5))) return fail(ctx, B200H_E_INVALID, "flags select neither SHA256 nor MD5");
@@ -854,23 +1127,21 @@ int b200h_stream_new(b200h_ctx* ctx, uint32_t flags, b200h_stream** out) {
     if (!s) return fail(ctx, B200H_E_NOMEM, "out of host memory");
     s->ctx = ctx;
     s->flags = flags & 3u;
-    s->cap = size_t(1) << 20;
-    s->hbuf = (uint8_t*)malloc(s->cap);
-    uint8_t* blk = nullptr;
-    if (!s->hbuf || cudaMalloc(&blk, s->cap + 2 * sizeof(ChainState) + 64 + 64) != cudaSuccess) {
-        cudaGetLastError();
-        free(s->hbuf);
+    s->cap = ctx->stream_cap;
+    if (int rc = stream_res_acquire(ctx, &s->res)) {
         delete s;
-        return fail(ctx, B200H_E_NOMEM, "stream allocation failed");
+        return rc;
     }
+    uint8_t* blk = s->res.d;
+    s->hbuf = s->res.h;
     s->d_state = (ChainState*)blk;
-    s->d_meta = (uint64_t*)(blk + 2 * sizeof(ChainState));
-    s->d_out = blk + 2 * sizeof(ChainState) + 64;
-    s->d_buf = blk + 2 * sizeof(ChainState) + 128;
-    int rc = stream_write_iv(s);
-    if (rc) {
-        cudaFree(blk);
-        free(s->hbuf);
+    s->d_meta = (uint64_t*)(blk + kStreamMetaOff);
+    s->d_out = blk + kStreamOutOff;
+    s->d_plan = (uint32_t*)(blk + kStreamPlanOff);
+    s->d_ring = (uint32_t*)(blk + kStreamRingOff);
+    s->d_buf = blk + kStreamDataOff;
+    if (int rc = stream_write_iv(s)) {
+        stream_res_destroy(s->res);
         delete s;
         return rc;
     }
@@ -880,18 +1151,27 @@ int b200h_stream_new(b200h_ctx* ctx, uint32_t flags, b200h_stream** out) {
 
 int b200h_stream_update(b200h_stream* s, const uint8_t* data, uint64_t len) {
     if (!s) return B200H_E_INVALID;
+    B200H_RANGE("b200h_stream_update");
     b200h_ctx* ctx = s->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (len && !data) return fail(ctx, B200H_E_INVALID, "data is NULL");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (len && !data) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        return fail(ctx, B200H_E_INVALID, "data is NULL");
+    }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU_TRY(ctx, cudaSetDevice(ctx->device));
+    }
     s->total += len;
     while (len) {
+        if (s->fill == 0)
+            if (int rc = stream_wait_hbuf(s)) return rc;
         const size_t take = (size_t)std::min<uint64_t>(len, s->cap - s->fill);
         memcpy(s->hbuf + s->fill, data, take);
         s->fill += take;
         data += take;
         len -= take;
         if (s->fill == s->cap) {
+            std::lock_guard<std::mutex> lk(ctx->mu);  // enqueue only: microseconds
             if (int rc = stream_absorb(s, s->cap)) return rc;
             s->fill = 0;
         }
@@ -901,20 +1181,28 @@ int b200h_stream_update(b200h_stream* s, const uint8_t* data, uint64_t len) {
 
 int b200h_stream_digest(b200h_stream* s, uint8_t sha256_out[32], uint8_t md5_out[16]) {
     if (!s) return B200H_E_INVALID;
+    B200H_RANGE("b200h_stream_digest");
     b200h_ctx* ctx = s->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
-    // finalise on a scratch copy of the state so that further updates remain possible
-    const uint64_t meta[2] = {0, s->fill};
-    CU_TRY(ctx, cudaMemcpyAsync(s->d_state + 1, s->d_state, sizeof(ChainState), cudaMemcpyDeviceToDevice, ctx->s_comp));
-    if (s->fill) CU_TRY(ctx, cudaMemcpyAsync(s->d_buf, s->hbuf, s->fill, cudaMemcpyHostToDevice, ctx->s_comp));
-    CU_TRY(ctx, cudaMemcpyAsync(s->d_meta, meta, sizeof meta, cudaMemcpyHostToDevice, ctx->s_comp));
-    if (int rc = enqueue_device_batch(ctx, s->d_buf, s->d_meta, s->d_meta + 1, 1, s->flags, s->d_out, s->d_out + 32,
-                                      nullptr, s->d_state + 1, ctx->s_comp))
-        return rc;
-    uint8_t host[48];
-    CU_TRY(ctx, cudaMemcpyAsync(host, s->d_out, 48, cudaMemcpyDeviceToHost, ctx->s_comp));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->s_comp));
+    cudaStream_t st = s->res.st;
+    uint8_t* host = s->hbuf + s->cap + 64;  // pinned: the copy below only enqueues
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU_TRY(ctx, cudaSetDevice(ctx->device));
+        // finalise on a scratch copy of the state so that further updates remain possible
+        uint64_t* h_meta = reinterpret_cast<uint64_t*>(s->hbuf + s->cap) + 2;  // pinned slot of the digest launch
+        h_meta[0] = 0;
+        h_meta[1] = s->fill;
+        const uint64_t hlen = s->fill;
+        CU_TRY(ctx, cudaMemcpyAsync(s->d_state + 1, s->d_state, sizeof(ChainState), cudaMemcpyDeviceToDevice, st));
+        if (s->fill) CU_TRY(ctx, cudaMemcpyAsync(s->d_buf, s->hbuf, s->fill, cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaMemcpyAsync(s->d_meta + 2, h_meta, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        if (int rc = enqueue_device_batch(ctx, s->d_buf, s->d_meta + 2, s->d_meta + 3, 1, s->flags, s->d_out, s->d_out + 32,
+                                          nullptr, s->d_state + 1, st, &hlen, s->d_plan, s->d_ring))
+            return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(host, s->d_out, 48, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(st));  // outside the lock: other streams keep enqueueing meanwhile
+    s->h2d_pending = false;
     if (sha256_out && (s->flags & B200H_SHA256)) memcpy(sha256_out, host, 32);
     if (md5_out && (s->flags & B200H_MD5)) memcpy(md5_out, host + 32, 16);
     return 0;
@@ -929,14 +1217,14 @@ int b200h_stream_reset(b200h_stream* s) {
 
 void b200h_stream_free(b200h_stream* s) {
     if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->res.st);
+    cudaGetLastError();
     {
         std::lock_guard<std::mutex> lk(s->ctx->mu);
-        cudaSetDevice(s->ctx->device);
-        cudaStreamSynchronize(s->ctx->s_comp);
-        cudaFree(s->d_state);
-        cudaGetLastError();
+        if (s->ctx->stream_pool.size() < 64) s->ctx->stream_pool.push_back(s->res);
+        else stream_res_destroy(s->res);
     }
-    free(s->hbuf);
     delete s;
 }
 
@@ -1016,6 +1304,20 @@ int b200h_last_outlier_count(b200h_ctx* ctx, uint32_t* count_out) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     *count_out = ctx->last_outliers;
     return 0;
+}
+
+int b200h_combine_stats(b200h_ctx* ctx, uint64_t* groups_out, uint64_t* requests_out) {
+    if (!ctx) return B200H_E_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->combiner.m);
+    if (groups_out) *groups_out = ctx->combiner.groups;
+    if (requests_out) *requests_out = ctx->combiner.requests;
+    return 0;
+}
+
+uint64_t b200h_plan_sync_count(b200h_ctx* ctx) {
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->plan_syncs;
 }
 
 uint64_t b200h_launch_count(b200h_ctx* ctx) {

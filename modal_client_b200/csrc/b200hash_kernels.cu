@@ -1137,13 +1137,44 @@ chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
     }
 }
 
-// ------------------------------------------------------------------------------------ trim_kernel
+// ------------------------------------------------------------------------------------ trim kernels
 // Reference semantics (blob_utils.py:667-705): index just past the last non-zero byte, 0 when the
-// message is empty or all zero.  One warp per message scanning backwards, 4 x 16 B per lane in flight.
+// message is empty or all zero.  Two kernels:
+//   trim_probe_kernel  one warp per message scanning backwards from the end, 2 KiB (4 x 16 B per lane) per step.
+//                      Most messages end in a non-zero byte and are settled by the first step, so the common case
+//                      reads <= 2 KiB per message.  A message that is still all zero after kTrimProbeSteps steps
+//                      with >= kTrimWideMin bytes left is handed to the wide scan: its remaining range is cut into
+//                      kTrimChunk-byte work items (nearest the end first) appended to a device-side list.
+//   trim_wide_kernel   persistent CTAs pull those items from a counter; a CTA scans its chunk backwards 32 KiB per
+//                      step (256 threads x 8 x 16 B in flight), publishes what it finds with atomicMax on
+//                      trimmed[m] and gives up as soon as a later chunk of the same message has found a byte.
+//                      Long zero runs (blank volumefs2 blocks, sparse files) are therefore read by every SM at once
+//                      -- this is the one HBM-bound kernel on the path -- instead of by one warp walking 2 KiB per
+//                      dependent step (round 1: ~1 280 warps x 2 KiB in flight for 1 280 blank 8 MiB blocks).
+
+constexpr int kTrimProbeSteps = 8;              // 16 KiB settled by the probe warp before a message goes wide
+constexpr uint64_t kTrimWideMin = 256 * 1024;   // shorter remainders stay on the probe warp
+constexpr uint64_t kTrimChunk = 512 * 1024;     // bytes per wide work item (multiple of the 32 KiB step)
+constexpr int kTrimWideThreads = 256;
+constexpr int kTrimWideLoads = 8;               // 16-byte loads in flight per thread
+constexpr int kTrimWideCtasPerSm = 4;           // 64 registers per thread; 4 x 32 KiB in flight per SM
+constexpr uint64_t kTrimWideStep = (uint64_t)kTrimWideThreads * kTrimWideLoads * 16;
+
+// 1 + index (within the message, `pos` = index of the granule's first byte) of the last non-zero byte of a 16-byte
+// granule, 0 if it is all zero
+__device__ __forceinline__ uint64_t granule_last_nonzero(const uint4& v, uint64_t pos) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint64_t best = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (w[q]) best = pos + 4 * q + (4 - (__clz(w[q]) >> 3));
+    return best;
+}
 
 __global__ void __launch_bounds__(256)
-trim_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
-            uint64_t n, uint64_t* __restrict__ trimmed) {
+trim_probe_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
+                  uint64_t n, uint64_t* __restrict__ trimmed, unsigned long long* __restrict__ wctl,
+                  TrimWideEntry* __restrict__ wlist) {
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t m = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); m < n; m += warps) {
@@ -1160,7 +1191,14 @@ trim_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, 
             if (mask) found = end - (uint64_t)(__ffs(mask) - 1);
             end -= tail;
         }
+        int steps = 0;
+        bool wide = false;
         while (!found && end >= 16) {
+            if (steps == kTrimProbeSteps && end >= kTrimWideMin) {
+                wide = true;
+                break;
+            }
+            ++steps;
             // granules [end-16*(k+1), end-16*k) for k = lane + 32*u, u = 0..3 (nearest the end first)
             uint4 v[4];
             uint64_t pos[4];
@@ -1168,24 +1206,36 @@ trim_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, 
             for (int u = 0; u < 4; ++u) {
                 const uint64_t k = (uint64_t)lane + 32u * u;
                 const bool ok = 16 * (k + 1) <= end;  // p + end is 16B-aligned here
-                pos[u] = ok ? end - 16 * (k + 1) : ~0ull;
+                pos[u] = ok ? end - 16 * (k + 1) : 0;
                 v[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(p + pos[u])) : make_uint4(0, 0, 0, 0);
             }
             uint64_t best = 0;
 #pragma unroll
             for (int u = 3; u >= 0; --u) {
-                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (w[q]) {
-                        const uint64_t cand = pos[u] + 4 * q + (4 - (__clz(w[q]) >> 3));
-                        best = cand > best ? cand : best;
-                    }
+                const uint64_t cand = granule_last_nonzero(v[u], pos[u]);
+                best = cand > best ? cand : best;
             }
             best = warp_max_u64(best);
             if (best) found = best;
             const uint64_t whole = end & ~15ull;
             end -= whole < 2048 ? whole : 2048;
+        }
+        if (wide) {
+            // [0, end) is still unknown and p + end is 16-byte aligned: cut it into chunks, nearest the end first.
+            // One 64-bit atomic reserves the list slot (high word) and the item range (low word) together, so the
+            // list is sorted by first item and the wide kernel can binary-search it.
+            if (lane == 0) {
+                const uint64_t k = (end + kTrimChunk - 1) / kTrimChunk;
+                const unsigned long long old = atomicAdd(&wctl[0], (1ull << 32) | (unsigned long long)k);
+                TrimWideEntry e;
+                e.msg = m;
+                e.end = end;
+                e.first_item = (uint32_t)old;
+                e.items = (uint32_t)k;
+                wlist[old >> 32] = e;
+                trimmed[m] = 0;  // the answer if everything left is zero; raised by atomicMax in the wide kernel
+            }
+            continue;
         }
         if (!found && end > 0 && end < 16) {
             // fewer than 16 bytes remain at the (unaligned) head of the message
@@ -1198,24 +1248,149 @@ trim_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, 
     }
 }
 
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kTrimWideThreads, kTrimWideCtasPerSm)
+trim_wide_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, uint64_t* __restrict__ trimmed,
+                 unsigned long long* __restrict__ wctl, const TrimWideEntry* __restrict__ wlist) {
+    __shared__ uint32_t sh_item;
+    __shared__ uint64_t sh_best[kTrimWideThreads / 32];
+    const unsigned long long ctl = wctl[0];  // written by the probe kernel (earlier in the stream)
+    const uint32_t total = (uint32_t)ctl, entries = (uint32_t)(ctl >> 32);
+    if (!total) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned long long* best_of = reinterpret_cast<unsigned long long*>(trimmed);
+    for (;;) {
+        __syncthreads();  // sh_item / sh_best of the previous item are no longer read
+        if (tid == 0) sh_item = (uint32_t)atomicAdd(&wctl[1], 1ull);
+        __syncthreads();
+        const uint32_t item = sh_item;
+        if (item >= total) return;
+        // entry with the largest first_item <= item
+        uint32_t lo = 0, hi = entries;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (wlist[mid].first_item <= item) lo = mid;
+            else hi = mid;
+        }
+        const TrimWideEntry e = wlist[lo];
+        const uint64_t j = item - e.first_item;              // 0 = the chunk nearest the end
+        const uint64_t c_hi = e.end - j * kTrimChunk;         // p + c_hi is 16-byte aligned
+        const uint64_t c_lo = c_hi > kTrimChunk ? c_hi - kTrimChunk : 0;
+        const uint8_t* p = base + off[e.msg];
+        // aligned part of the chunk: [a_lo, c_hi); the < 16 unaligned head bytes [0, a_lo) exist only when c_lo == 0
+        // p + c_hi is aligned, so p & 15 == (-c_hi) & 15 and the bytes before the first aligned address number c_hi & 15
+        const uint64_t head = c_lo ? 0 : (c_hi & 15u);
+        const uint64_t a_lo = c_lo + head;
+        uint64_t cur = c_hi;
+        uint64_t found = 0;
+        bool superseded = false;
+        while (cur > a_lo) {
+            uint4 v[kTrimWideLoads];
+            uint64_t pos[kTrimWideLoads];
+#pragma unroll
+            for (int u = 0; u < kTrimWideLoads; ++u) {
+                const uint64_t k = (uint64_t)tid + (uint64_t)kTrimWideThreads * u;
+                const bool ok = cur >= a_lo + 16 * (k + 1);
+                pos[u] = ok ? cur - 16 * (k + 1) : 0;
+                v[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(p + pos[u])) : make_uint4(0, 0, 0, 0);
+            }
+            uint64_t best = 0;
+#pragma unroll
+            for (int u = 0; u < kTrimWideLoads; ++u) {
+                const uint64_t cand = granule_last_nonzero(v[u], pos[u]);
+                best = cand > best ? cand : best;
+            }
+            // a later chunk of this message already holds a non-zero byte: nothing in here can matter
+            const bool stale = tid == 0 && ld_volatile_u64(&best_of[e.msg]) > c_hi;
+            const int flags = __syncthreads_or((best ? 1 : 0) | (stale ? 2 : 0));
+            if (flags & 2) {
+                superseded = true;
+                break;
+            }
+            if (flags & 1) {
+                best = warp_max_u64(best);
+                if (lane == 0) sh_best[wid] = best;
+                __syncthreads();
+                if (tid == 0) {
+                    uint64_t b = 0;
+                    for (int w = 0; w < kTrimWideThreads / 32; ++w) b = sh_best[w] > b ? sh_best[w] : b;
+                    found = b;
+                }
+                break;
+            }
+            const uint64_t span = cur - a_lo;
+            cur -= span < kTrimWideStep ? span : kTrimWideStep;
+        }
+        if (tid == 0) {
+            if (!found && !superseded && head) {
+                // the unaligned first bytes of the message
+                for (uint64_t i = head; i > 0; --i)
+                    if (p[i - 1]) {
+                        found = i;
+                        break;
+                    }
+            }
+            if (found) atomicMax(&best_of[e.msg], (unsigned long long)found);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ plan kernels
 // Bucket key: exact block count below 16, then 8 sub-buckets per power of two (<= 12.5 % spread inside
 // a bucket, so lanes of a warp run nearly equal trip counts).  Buckets are laid out longest first.
 
-__device__ __forceinline__ uint32_t plan_bucket(uint64_t len) {
+__host__ __device__ __forceinline__ int plan_log2_u64(uint64_t v) {  // floor(log2 v), v > 0
+#ifdef __CUDA_ARCH__
+    return 63 - __clzll((long long)v);
+#else
+    return 63 - __builtin_clzll(v);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint32_t plan_bucket(uint64_t len) {
     const uint64_t nb = (len >> 6) + 1;
     if (nb < 16) return (uint32_t)nb;
-    const int e = 63 - __clzll((long long)nb);
+    const int e = plan_log2_u64(nb);
     const uint32_t b = 16u + (uint32_t)(e - 4) * 8u + (uint32_t)((nb >> (e - 3)) & 7u);
     return b < (uint32_t)kPlanBuckets ? b : (uint32_t)kPlanBuckets - 1;
 }
 
 // smallest block count that maps to bucket b (inverse of plan_bucket)
-__device__ __forceinline__ uint64_t plan_bucket_min_blocks(uint32_t b) {
+__host__ __device__ __forceinline__ uint64_t plan_bucket_min_blocks(uint32_t b) {
     if (b < 16) return b;
     const uint32_t e = (b - 16) / 8 + 4, mant = (b - 16) % 8;
     if (e - 3 >= 60) return ~0ull;  // buckets no 64-bit length can reach: saturate instead of wrapping around
     return (uint64_t)(8 + mant) << (e - 3);
+}
+
+// Host mirror of plan_hist_kernel + plan_scan_kernel's chain selection: how many of these messages the planner will
+// hand to the chain kernel.  Same integer arithmetic on the same lengths, so the answer is the device's; callers
+// that hold the lengths on the host use it to size the chain launch WITHOUT reading qctl[3] back (no stream
+// synchronisation inside an enqueue).  B200H_VERIFY_PLAN=1 makes the API cross-check it against the device.
+uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain) {
+    if (!n || !max_chain) return 0;
+    uint64_t longest = 0;
+    unsigned long long total = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        longest = len[i] > longest ? len[i] : longest;
+        total += (len[i] >> 6) + 1;
+    }
+    if ((longest >> 6) + 1 < kChainMinBlocks) return 0;  // nothing can reach rule (1)
+    unsigned long long thr = total / kChainRatio;
+    if (thr < kChainMinBlocks) thr = kChainMinBlocks;
+    const uint32_t top = plan_bucket(longest);
+    const unsigned long long half = plan_bucket_min_blocks(top) / 2;
+    if (thr < half) thr = half;
+    // messages in buckets whose lower bound reaches thr (bucket lower bounds are monotone in the bucket index)
+    uint64_t count = 0;
+    for (uint64_t i = 0; i < n; ++i)
+        if (plan_bucket_min_blocks(plan_bucket(len[i])) >= thr) ++count;
+    return count <= max_chain ? (uint32_t)count : 0u;
 }
 
 __global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ hist,
@@ -1343,6 +1518,8 @@ __global__ void fill_synth_kernel(uint8_t* __restrict__ dst, uint64_t nbytes, ui
 
 // --------------------------------------------------------------------------------- launch wrappers
 
+static int g_sm_count = 148;
+
 static int grid_for(uint64_t n, int threads, int cap) {
     uint64_t g = (n + threads - 1) / threads;
     if (g < 1) g = 1;
@@ -1350,13 +1527,15 @@ static int grid_for(uint64_t n, int threads, int cap) {
 }
 
 int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n, uint64_t* trimmed,
-                cudaStream_t st) {
+                unsigned long long* wctl, TrimWideEntry* wlist, cudaStream_t st) {
     if (!n) return 0;
-    trim_kernel<<<grid_for(n * 32, 256, 148 * 8), 256, 0, st>>>(base, off, len, n, trimmed);
-    return 1;
+    cudaMemsetAsync(wctl, 0, 2 * sizeof(unsigned long long), st);
+    trim_probe_kernel<<<grid_for(n * 32, 256, g_sm_count * 8), 256, 0, st>>>(base, off, len, n, trimmed, wctl, wlist);
+    trim_wide_kernel<<<g_sm_count * kTrimWideCtasPerSm, kTrimWideThreads, 0, st>>>(base, off, trimmed, wctl, wlist);
+    return 2;
 }
 
-static int g_sm_count = 148;
+
 static int g_lane_ctas_per_sm[3] = {B200H_LANE_MIN_CTAS, B200H_LANE_MIN_CTAS, B200H_LANE_MIN_CTAS};  // [sha+md5, sha, md5]
 
 uint32_t ring_capacity(uint64_t n) {

@@ -28,8 +28,19 @@ constexpr int kPlanScratchWords = 2 * kPlanBuckets + 8;  // hist, cursor, qctl[4
 
 // Launch wrappers (defined in b200hash_kernels.cu).  All asynchronous on `st`.
 // Every wrapper returns the number of kernels it launched (for gpu_launches accounting).
+// One entry per message the trim probe hands to the wide scan: bytes [0, end) of message `msg` are still unknown,
+// cut into `items` chunks (nearest the end first) numbered from `first_item`.
+struct TrimWideEntry {
+    uint64_t msg;
+    uint64_t end;
+    uint32_t first_item;
+    uint32_t items;
+};
+// wctl: 2 x u64 control block {entries << 32 | items, next item}; wlist: n entries.
 int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n, uint64_t* trimmed,
-                cudaStream_t st);
+                unsigned long long* wctl, TrimWideEntry* wlist, cudaStream_t st);
+// The planner's outlier count for these lengths, computed on the host (mirror of plan_scan_kernel's selection).
+uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain);
 uint32_t ring_capacity(uint64_t n);  // power of two >= max(n, 32): entries of the work-queue ring
 // scratch layout (uint32 words): hist[kPlanBuckets] | cursor[kPlanBuckets] | qctl[4] | total_blocks (u64) | pad
 inline int* plan_qctl(uint32_t* scratch) { return reinterpret_cast<int*>(scratch + 2 * kPlanBuckets); }

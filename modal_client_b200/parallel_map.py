@@ -1,10 +1,21 @@
 """The map input pump: raw (args, kwargs) -> FunctionPutInputsItem -> batched FunctionPutInputs.
 
-Mirrors ``InputPreprocessor`` / ``InputPumper`` of the reference (py/modal/parallel_map.py:90-198) on the
-part that touches the hash path.  The reference builds items one input at a time under an ordered 20-way
-async map, which means one hashlib pass per payload on the event-loop thread; here the preprocessor drains
-whatever is queued (up to ``HASH_WINDOW`` inputs) and hands the whole window to
-``function_utils.create_inputs_batch`` -- one GPU hash batch per window -- preserving input order.
+Mirrors ``InputPreprocessor`` / ``InputPumper`` of the reference (py/modal/parallel_map.py:90-198) and the
+input-plane variant's ``create_input`` / ``drain_input_generator`` (:707-736) on the part that touches the hash path.
+The reference builds items one input at a time under an ordered 20-way async map, which means one hashlib pass per
+payload on the event-loop thread (``blob_upload_with_r2_failure_info`` -> ``get_upload_hashes``,
+_utils/blob_utils.py:338-352).  Here the preprocessor is a three-stage pipeline that keeps the reference's
+observable behaviour -- items leave in input order, each as soon as its own blob is uploaded, at most
+``BLOB_MAX_PARALLELISM`` uploads in flight -- and feeds the GPU what it needs:
+
+  collect   whatever is already queued, up to a BYTE budget (``HASH_WINDOW_BYTES``; one lone input is a window of
+            one: nothing waits for company), serialized as it is taken;
+  hash      all payloads of the window that must be blobified -> ONE GPU batch, on a worker thread
+            (the library releases the GIL); up to ``HASH_WINDOWS_IN_FLIGHT`` windows on as many contexts, so
+            packing + H2D of window k+1 overlaps the kernel of window k and the uploads of window k-1;
+  upload    BlobCreate + PUT per payload, ``BLOB_MAX_PARALLELISM`` at a time, results emitted in order as they
+            complete (``bounded_map_ordered``).
+
 The retry / output-polling state machine of the reference (:1320-1644) is control plane and not rebuilt.
 """
 from __future__ import annotations
@@ -13,19 +24,144 @@ import asyncio
 from collections.abc import Callable
 from typing import Any
 
-from . import _wire
+from . import _backend, _wire, blob_utils, hash_utils
 from ._logging import logger
-from .function_utils import create_inputs_batch
+from .async_utils import bounded_map_ordered
+from .function_utils import _blob_item, _function_fields, _inline_item, serialize_data_format, should_upload
 
 MAP_INVOCATION_CHUNK_SIZE = 49  # inputs per FunctionPutInputs request (sync map)
 SPAWN_MAP_INVOCATION_CHUNK_SIZE = 512
-HASH_WINDOW = 1024  # inputs gathered into one GPU hash batch
+HASH_WINDOW_BYTES = 1 << 30  # payload bytes gathered into one GPU hash batch ...
+HASH_WINDOW_ITEMS = 65536  # ... and at most this many inputs (both: of what is ALREADY queued)
+HASH_WINDOWS_IN_FLIGHT = 2  # windows being hashed at the same time (one library context each)
+PUMP_INPUTS_MAX_RETRY_DELAY = 15.0  # reference :67 (RESOURCE_EXHAUSTED back-off ceiling of the pumper)
+
+_END = object()
+
+
+class _Window:
+    """One hash window: the serialized payloads of consecutive inputs and which of them go to blob storage."""
+
+    __slots__ = ("first_idx", "payloads", "big", "hashes")
+
+    def __init__(self, first_idx: int):
+        self.first_idx = first_idx
+        self.payloads: list[bytes] = []
+        self.big: list[int] = []  # positions (within the window) of payloads above the threshold
+        self.hashes = None  # future -> sequence of UploadHashes, one per entry of `big`
+
+
+class _WindowedInputPipeline:
+    """collect -> hash -> upload over a raw-input queue; ``items()`` yields the wire items in input order."""
+
+    def __init__(self, raw_input_queue, stub, function, *, first_idx: int = 0, on_created: Callable[[int], None] | None = None,
+                 make_item: Callable[[Any], Any] | None = None, function_call_invocation_type=None,
+                 serializer: Callable[[Any], bytes] | None = None, payload_format: str | None = None):
+        self.q = raw_input_queue
+        self.stub = stub
+        self.method_name, self.max_bytes, self.data_format = _function_fields(function, payload_format)
+        self.invocation_type = function_call_invocation_type
+        self.serializer = serializer
+        self.next_idx = first_idx
+        self.first_idx = first_idx
+        self.on_created = on_created or (lambda n: None)
+        self.make_item = make_item or (lambda item: item)
+        self.windows_hashed = 0
+        self.digest_tables: list | None = None  # set to [] to keep every window's (sha[n,32], md5[n,16]) arrays
+
+    # ---- stage 1: collect ----------------------------------------------------------------------------------
+    def _take(self, win: _Window, argskwargs) -> int:
+        payload = self.serializer(argskwargs) if self.serializer else serialize_data_format(argskwargs, self.data_format)
+        if should_upload(len(payload), self.max_bytes, self.invocation_type):
+            win.big.append(len(win.payloads))
+        win.payloads.append(payload)
+        self.next_idx += 1
+        self.on_created(self.next_idx - self.first_idx)
+        return len(payload)
+
+    async def _next_window(self) -> tuple[_Window | None, bool]:
+        """Block for one raw input, then take what is already queued, up to the byte / item budget."""
+        first = await self.q.get()
+        if first is None:
+            return None, True
+        win = _Window(self.next_idx)
+        nbytes = self._take(win, first)
+        finished = False
+        while nbytes < HASH_WINDOW_BYTES and len(win.payloads) < HASH_WINDOW_ITEMS:
+            try:
+                nxt = self.q.get_nowait()
+            except asyncio.QueueEmpty:
+                break
+            if nxt is None:
+                finished = True
+                break
+            nbytes += self._take(win, nxt)
+        return win, finished
+
+    # ---- stage 2: hash -------------------------------------------------------------------------------------
+    async def _collect_and_hash(self, out: asyncio.Queue):
+        loop = asyncio.get_running_loop()
+        pool = _backend.context_pool(HASH_WINDOWS_IN_FLIGHT)
+        free = asyncio.Queue()
+        for c in pool:
+            free.put_nowait(c)
+        finished = False
+        try:
+            while not finished:
+                win, finished = await self._next_window()
+                if win is None:
+                    break
+                if win.big:
+                    ctx = await free.get()  # at most one batch per context at a time
+                    big_payloads = [win.payloads[i] for i in win.big]
+                    fut = loop.run_in_executor(None, lambda c=ctx, p=big_payloads: hash_utils.get_upload_hashes_many(p, ctx=c))
+                    fut.add_done_callback(lambda _f, c=ctx: free.put_nowait(c))
+                    win.hashes = fut
+                    self.windows_hashed += 1
+                await out.put(win)
+        finally:
+            await out.put(_END)
+
+    # ---- stage 3: upload, emit in order ---------------------------------------------------------------------
+    async def items(self):
+        handoff: asyncio.Queue = asyncio.Queue(maxsize=HASH_WINDOWS_IN_FLIGHT)
+        producer = asyncio.ensure_future(self._collect_and_hash(handoff))
+        try:
+            while True:
+                win = await handoff.get()
+                if win is _END:
+                    break
+                hashes = await win.hashes if win.hashes is not None else ()
+                if self.digest_tables is not None and win.hashes is not None:
+                    self.digest_tables.append((hashes._sha, hashes._md5))
+                big_pos = {pos: k for k, pos in enumerate(win.big)}
+
+                async def build(pos, win=win, hashes=hashes, big_pos=big_pos):
+                    payload = win.payloads[pos]
+                    win.payloads[pos] = None  # the window must not pin every payload until its last upload is done
+                    k = big_pos.get(pos)
+                    if k is None:
+                        return _inline_item(win.first_idx + pos, payload, self.data_format, self.method_name)
+                    upload = await blob_utils._blob_upload(hashes[k], payload, self.stub)
+                    return _blob_item(win.first_idx + pos, upload, self.data_format, self.method_name)
+
+                async for item in bounded_map_ordered(range(len(win.payloads)), build, blob_utils.BLOB_MAX_PARALLELISM):
+                    yield self.make_item(item)
+            await producer  # surfaces a collector failure
+        finally:
+            if not producer.done():
+                producer.cancel()
+                await asyncio.gather(producer, return_exceptions=True)
 
 
 class InputPreprocessor:
+    """Constructs FunctionPutInputsItem objects from the raw-input queue and puts them in the processed-input queue
+    (reference :90-147)."""
+
     def __init__(self, client, *, raw_input_queue, processed_input_queue: asyncio.Queue, function,
                  created_callback: Callable[[int], None] = lambda n: None,
-                 done_callback: Callable[[], None] = lambda: None):
+                 done_callback: Callable[[], None] = lambda: None,
+                 serializer: Callable[[Any], bytes] | None = None):
         self.client = client
         self.function = function
         self.inputs_created = 0
@@ -33,36 +169,23 @@ class InputPreprocessor:
         self.processed_input_queue = processed_input_queue
         self.created_callback = created_callback
         self.done_callback = done_callback
+        self.serializer = serializer  # None: the negotiated payload format's serializer (pickle / CBOR)
+        self.hash_batches = 0
+        self.keep_digest_tables = False  # True: ``digest_tables`` collects each window's (sha, md5) numpy tables
+        self.digest_tables: list = []
 
-    async def _next_window(self) -> tuple[list, bool]:
-        """Block for one raw input, then take everything else that is already queued (<= HASH_WINDOW)."""
-        window, finished = [], False
-        first = await self.raw_input_queue.get()
-        if first is None:
-            return window, True
-        window.append(first)
-        while len(window) < HASH_WINDOW:
-            try:
-                nxt = self.raw_input_queue.get_nowait()
-            except asyncio.QueueEmpty:
-                break
-            if nxt is None:
-                finished = True
-                break
-            window.append(nxt)
-        return window, finished
+    def _created(self, n: int) -> None:
+        self.inputs_created = n
+        self.created_callback(n)
 
     async def drain_input_generator(self):
-        finished = False
-        while not finished:
-            window, finished = await self._next_window()
-            if window:
-                first_idx = self.inputs_created
-                self.inputs_created += len(window)
-                self.created_callback(self.inputs_created)
-                items = await create_inputs_batch(window, self.client.stub, function=self.function, first_idx=first_idx)
-                for item in items:
-                    await self.processed_input_queue.put(item)
+        pipe = _WindowedInputPipeline(self.raw_input_queue, self.client.stub, self.function, first_idx=0,
+                                      on_created=self._created, serializer=self.serializer)
+        if self.keep_digest_tables:
+            pipe.digest_tables = self.digest_tables
+        async for item in pipe.items():
+            await self.processed_input_queue.put(item)
+        self.hash_batches = pipe.windows_hashed
         await self.processed_input_queue.put(None)  # end-of-queue marker for the pumper
         self.done_callback()
         yield
@@ -88,21 +211,93 @@ async def queue_batch_iterator(q: asyncio.Queue, max_batch_size: int = 100, debo
         batch.append(item)
 
 
+def _is_resource_exhausted(exc: BaseException) -> bool:
+    """grpclib's ``GRPCError(Status.RESOURCE_EXHAUSTED)`` (status value 8), recognised structurally so that this
+    module does not need grpclib installed."""
+    status = getattr(exc, "status", None)
+    return getattr(status, "name", None) == "RESOURCE_EXHAUSTED" or getattr(status, "value", status) == 8
+
+
 class InputPumper:
+    """Reads FunctionPutInputsItems from a queue and sends them to the server (reference :150-214), including the
+    hooks of the map state machine: ``map_items_manager.add_items`` before the RPC (items are SENDING),
+    ``handle_put_inputs_response`` after it (WAITING_FOR_OUTPUT with the server's input ids), and unlimited retries
+    with capped exponential back-off while the server answers RESOURCE_EXHAUSTED (``_function_inputs_retry``)."""
+
     def __init__(self, client, *, input_queue: asyncio.Queue, function, function_call_id: str,
-                 max_batch_size: int = MAP_INVOCATION_CHUNK_SIZE):
+                 max_batch_size: int = MAP_INVOCATION_CHUNK_SIZE, map_items_manager=None):
         self.client = client
         self.function = function
+        self.map_items_manager = map_items_manager
         self.input_queue = input_queue
         self.inputs_sent = 0
         self.function_call_id = function_call_id
         self.max_batch_size = max_batch_size
+        self.resource_exhausted_retries = 0
+
+    async def _put_inputs(self, request):
+        delay = 0.1
+        while True:
+            try:
+                return await self.client.stub.FunctionPutInputs(request)
+            except Exception as exc:  # noqa: BLE001 - filtered below
+                if not _is_resource_exhausted(exc):
+                    raise
+                self.resource_exhausted_retries += 1
+                if self.resource_exhausted_retries % 8 == 0:
+                    name = getattr(self.function, "_function_name", "")
+                    logger.warning(f"Warning: map progress for function {name} is limited."
+                                   " Common bottlenecks include slow iteration over results, or function backlogs.")
+                await asyncio.sleep(delay)
+                delay = min(delay * 2, PUMP_INPUTS_MAX_RETRY_DELAY)
 
     async def pump_inputs(self):
+        assert self.client.stub
         async for items in queue_batch_iterator(self.input_queue, max_batch_size=self.max_batch_size):
+            if self.map_items_manager is not None:
+                await self.map_items_manager.add_items(items)
             request = _wire.FunctionPutInputsRequest(
                 function_id=getattr(self.function, "object_id", ""), inputs=items, function_call_id=self.function_call_id)
-            logger.debug(f"Pushing {len(items)} inputs to server. Queued: {self.input_queue.qsize()}.")
-            await self.client.stub.FunctionPutInputs(request)
+            logger.debug(f"Pushing {len(items)} inputs to server. Num queued inputs awaiting push is {self.input_queue.qsize()}.")
+            resp = await self._put_inputs(request)
             self.inputs_sent += len(items)
+            if self.map_items_manager is not None:
+                self.map_items_manager.handle_put_inputs_response(getattr(resp, "inputs", []))
+        yield
+
+
+# ------------------------------------------------------------------------------------------- input plane
+
+
+class InputPlanePreprocessor:
+    """The input half of ``_map_invocation_inputplane`` (reference :707-736): ``create_input`` numbers map calls from
+    1, wraps each FunctionPutInputsItem into a ``MapStartOrContinueItem`` and ``drain_input_generator`` pushes them,
+    in order, into the caller's timestamped queue; ``update_counters`` sees every created input and, at the end,
+    ``set_have_all_inputs=True``.  Same windowed GPU pipeline underneath."""
+
+    def __init__(self, client, *, raw_input_queue, queue, function,
+                 update_counters: Callable[..., None] = lambda **kw: None,
+                 serializer: Callable[[Any], bytes] | None = None):
+        self.client = client
+        self.function = function
+        self.raw_input_queue = raw_input_queue
+        self.queue = queue  # TimestampPriorityQueue-shaped: ``await queue.put(timestamp, item)``
+        self.update_counters = update_counters
+        self.serializer = serializer
+        self.inputs_created = 0
+
+    def _created(self, n: int) -> None:
+        delta, self.inputs_created = n - self.inputs_created, n
+        self.update_counters(created_delta=delta)
+
+    async def drain_input_generator(self):
+        import time
+
+        pipe = _WindowedInputPipeline(
+            self.raw_input_queue, self.client.stub, self.function, first_idx=1,  # 1-indexed map call idx (:708)
+            on_created=self._created, serializer=self.serializer,
+            make_item=lambda put_item: _wire.MapStartOrContinueItem(input=put_item))
+        async for q_item in pipe.items():
+            await self.queue.put(time.time(), q_item)
+        self.update_counters(set_have_all_inputs=True)  # all inputs have been read
         yield

@@ -118,3 +118,205 @@ def test_payload_format_negotiation(backend, monkeypatch):
             await function_utils._create_input((), {}, stub, function=unhydrated)
 
     asyncio.run(run())
+
+
+# ------------------------------------------------------------------------------------- round 2: windowed pipeline
+
+
+def test_bounded_map_ordered_streams_in_order_and_bounds_the_lookahead():
+    from modal_client_b200.async_utils import bounded_map_ordered
+
+    async def run():
+        in_flight, peak, started = 0, 0, []
+
+        async def fn(i):
+            nonlocal in_flight, peak
+            in_flight += 1
+            peak = max(peak, in_flight)
+            started.append(i)
+            await asyncio.sleep(0.02 if i == 0 else 0.001)  # item 0 is slow: successors finish first
+            in_flight -= 1
+            return i * i
+
+        out, seen_started_at_first_yield = [], None
+        async for r in bounded_map_ordered(range(40), fn, concurrency=4):
+            if seen_started_at_first_yield is None:
+                seen_started_at_first_yield = len(started)
+            out.append(r)
+        assert out == [i * i for i in range(40)] and peak <= 4
+        assert seen_started_at_first_yield <= 8 + 4  # at most 2 x concurrency results wait behind the slow one
+
+        async def boom(i):
+            if i == 5:
+                raise RuntimeError("five")
+            return i
+
+        got = []
+        with pytest.raises(RuntimeError, match="five"):
+            async for r in bounded_map_ordered(range(20), boom, concurrency=3):
+                got.append(r)
+        assert got == list(range(5))
+        assert [r async for r in bounded_map_ordered([], fn, 3)] == []
+
+    asyncio.run(run())
+
+
+def test_windows_are_byte_budgeted_and_items_stream_before_the_window_is_done(backend, monkeypatch):
+    """the pump must not hold a whole window back -- an input reaches the processed queue as soon as its
+    own upload (and its predecessors') is done -- and a window is capped by BYTES, not just by count."""
+    fn = types.SimpleNamespace(_use_method_name="", _max_object_size_bytes=1, _metadata=object(), object_id="fu-1")
+    monkeypatch.setattr(parallel_map, "HASH_WINDOW_BYTES", 64 * 1024)
+    uploads_done_when_first_item_arrived = []
+
+    class Stub:
+        def __init__(self):
+            self.created = 0
+
+        async def BlobCreate(self, req):
+            self.created += 1
+            return types.SimpleNamespace(WhichOneof=lambda _n: "upload_urls", blob_ids=["bl-x"],
+                                         upload_urls=types.SimpleNamespace(items=["null://"]))
+
+    put_calls = []
+
+    async def slow_put(url, payload, content_md5_b64=None, content_type=None):
+        put_calls.append(payload.size)
+        await asyncio.sleep(0.002)
+        return "etag"
+
+    monkeypatch.setattr(blob_utils, "_upload_to_s3_url", slow_put)
+
+    async def run():
+        stub = Stub()
+        client = types.SimpleNamespace(stub=stub)
+        raw, done = asyncio.Queue(), asyncio.Queue()
+        payloads = [bytes([i % 251]) * 4096 for i in range(100)]  # 400 KiB -> >= 6 windows of <= 64 KiB (+1 input)
+        for p in payloads:
+            raw.put_nowait(p)
+        raw.put_nowait(None)
+        created = []
+        pre = parallel_map.InputPreprocessor(client, raw_input_queue=raw, processed_input_queue=done, function=fn,
+                                             created_callback=created.append, serializer=lambda p: p)
+
+        async def drive():
+            async for _ in pre.drain_input_generator():
+                pass
+
+        task = asyncio.ensure_future(drive())
+        first = await done.get()
+        uploads_done_when_first_item_arrived.append(len(put_calls))
+        items = [first]
+        while (it := await done.get()) is not None:
+            items.append(it)
+        await task
+        assert [it.idx for it in items] == list(range(100)) and created == list(range(1, 101))
+        assert pre.hash_batches >= 6, pre.hash_batches
+        assert uploads_done_when_first_item_arrived[0] < 40, "the first item waited for its whole window"
+        assert stub.created == 100
+
+    asyncio.run(run())
+
+
+def test_pumper_map_items_manager_and_resource_exhausted_retry(monkeypatch):
+    """InputPumper hooks of the reference (py/modal/parallel_map.py:174-214): add_items before the RPC,
+    handle_put_inputs_response after it, unlimited retries while the server says RESOURCE_EXHAUSTED."""
+    monkeypatch.setattr(parallel_map, "PUMP_INPUTS_MAX_RETRY_DELAY", 0.01)
+    fn = types.SimpleNamespace(object_id="fu-1", _function_name="f")
+    events = []
+
+    class Exhausted(Exception):
+        status = types.SimpleNamespace(name="RESOURCE_EXHAUSTED", value=8)
+
+    class Manager:
+        async def add_items(self, items):
+            events.append(("add", [i.idx for i in items]))
+
+        def handle_put_inputs_response(self, inputs):
+            events.append(("resp", [i.idx for i in inputs]))
+
+    class Stub:
+        def __init__(self):
+            self.calls = 0
+
+        async def FunctionPutInputs(self, req):
+            self.calls += 1
+            if self.calls in (1, 2):
+                raise Exhausted()
+            if self.calls == 5:
+                raise ValueError("not retried")
+            return types.SimpleNamespace(inputs=[types.SimpleNamespace(idx=i.idx, input_id=f"in-{i.idx}") for i in req.inputs])
+
+    async def run():
+        q = asyncio.Queue()
+        for i in range(5):
+            q.put_nowait(_wire.FunctionPutInputsItem(idx=i))
+        q.put_nowait(None)
+        stub = Stub()
+        pump = parallel_map.InputPumper(types.SimpleNamespace(stub=stub), input_queue=q, function=fn,
+                                        function_call_id="fc", max_batch_size=2, map_items_manager=Manager())
+        with pytest.raises(ValueError, match="not retried"):
+            async for _ in pump.pump_inputs():
+                pass
+        assert pump.resource_exhausted_retries == 2 and pump.inputs_sent == 4
+        assert events[:4] == [("add", [0, 1]), ("resp", [0, 1]), ("add", [2, 3]), ("resp", [2, 3])]
+
+    asyncio.run(run())
+
+
+def test_inputplane_preprocessor_wraps_items_and_counts(backend):
+    """Input-plane variant (py/modal/parallel_map.py:707-736): 1-indexed map call idx, MapStartOrContinueItem wrapper,
+    timestamped queue, created_delta per input and set_have_all_inputs at the end."""
+    fn = types.SimpleNamespace(_use_method_name="", _max_object_size_bytes=20_000, _metadata=object(), object_id="fu-1")
+
+    class TsQueue:
+        def __init__(self):
+            self.items = []
+
+        async def put(self, ts, item):
+            assert isinstance(ts, float)
+            self.items.append(item)
+
+    async def run():
+        async with running_blob_server() as (host, store):
+            stub = FakeBlobStub(host)
+            raw = asyncio.Queue()
+            inputs = [((i, "y" * (3000 * i)), {}) for i in range(12)]  # the later ones cross the blob threshold
+            for ak in inputs:
+                raw.put_nowait(ak)
+            raw.put_nowait(None)
+            counters = []
+            q = TsQueue()
+            pre = parallel_map.InputPlanePreprocessor(types.SimpleNamespace(stub=stub), raw_input_queue=raw, queue=q,
+                                                      function=fn, update_counters=lambda **kw: counters.append(kw))
+            async for _ in pre.drain_input_generator():
+                pass
+            assert [it.input.idx for it in q.items] == list(range(1, 13))
+            assert all(isinstance(it, _wire.MapStartOrContinueItem) and it.attempt_token is None for it in q.items)
+            assert counters[:-1] == [{"created_delta": 1}] * 12 and counters[-1] == {"set_have_all_inputs": True}
+            blobbed = [it for it in q.items if it.input.input.args_blob_id]
+            assert 0 < len(blobbed) < 12
+            for it, ak in zip(q.items, inputs):
+                body = store.blobs[it.input.input.args_blob_id] if it.input.input.args_blob_id else it.input.input.args
+                assert pickle.loads(body) == ak
+            await blob_utils.ClientSessionRegistry.close_session()
+
+    asyncio.run(run())
+
+
+def test_bench_map_pump_leg_on_the_stand_in(fake_backend, monkeypatch):
+    """bench.py's headline e2e leg (real InputPreprocessor/InputPumper, null control plane) on a tiny set: every
+    BlobCreate carries the digests of exactly its payload, in order."""
+    import base64
+
+    import bench
+
+    monkeypatch.setattr(blob_utils, "_upload_to_s3_url", bench._null_put)
+    payloads = [bytes([i]) * (1000 + 37 * i) for i in range(50)]
+    stub = bench.NullStub()
+    dt, batches, tables = bench.run_map_pump(payloads, stub)
+    assert dt > 0 and batches >= 1 and stub.inputs_put == 50 and len(stub.blob_requests) == 50
+    for p, r in zip(payloads, stub.blob_requests):
+        assert r.content_length == len(p)
+        assert r.content_sha256_base64 == base64.b64encode(hashlib.sha256(p).digest()).decode()
+        assert r.content_md5 == base64.b64encode(hashlib.md5(p).digest()).decode()
+    assert sum(len(t[0]) for t in tables) == 50
