@@ -42,6 +42,7 @@ from ._backend import get_context
 from ._logging import logger
 from ._wire import BlobCreateRequest
 from .async_utils import asyncnullcontext, bounded_map, gather_cancel_on_error, retry
+from .bytes_io_segment_payload import BytesIOSegmentPayload, KnownBytesBody
 from .exception import ExecutionError
 from .hash_utils import UploadHashes, get_upload_hashes
 from .http_utils import ClientSessionRegistry
@@ -163,13 +164,14 @@ async def _upload_to_s3_url(
     """PUT one payload; returns the object's ETag after checking it against the local MD5
     (reference :110-156: S3's single-part ETag is the quoted MD5 hex of the body)."""
     with payload.reset_on_error():
+        body = payload.as_payload() if isinstance(payload, KnownBytesBody) else payload
         headers = {}
         if content_md5_b64 and use_md5(upload_url):
             headers["Content-MD5"] = content_md5_b64
         if content_type:
             headers["Content-Type"] = content_type
         async with ClientSessionRegistry.get_session().put(
-            upload_url, data=payload, headers=headers, skip_auto_headers=["content-type"] if content_type is None else []
+            upload_url, data=body, headers=headers, skip_auto_headers=["content-type"] if content_type is None else []
         ) as resp:
             if resp.status == 503:  # S3 SlowDown
                 logger.debug("Received SlowDown signal from S3, sleeping for 1 second before retrying.")
@@ -214,8 +216,6 @@ async def perform_multipart_upload(
     progress_report_cb: Callable | None = None,
     byte_budget: _ByteBudget | None = None,
 ) -> None:
-    from .bytes_io_segment_payload import BytesIOSegmentPayload
-
     # 1. hash every part on the GPU before sending anything
     start_pos = data_file.tell() if isinstance(data_file, BytesIO) else 0
     part_md5, expected_etag = await asyncio.to_thread(
@@ -354,15 +354,16 @@ async def _blob_upload(
         async def send_single(url):
             nonlocal payload
             if payload is None:
-                from .bytes_io_segment_payload import BytesIOSegmentPayload
-
                 # the whole-blob MD5 is already in upload_hashes: hand it to the payload instead of re-hashing
                 raw = getattr(upload_hashes, "md5_raw", None)
                 if raw is None and _is_real_md5(upload_hashes):
                     raw = bytes.fromhex(upload_hashes.md5_hex())
-                payload = BytesIOSegmentPayload(
-                    reader if reader is not None else BytesIO(data), segment_start=0, segment_length=content_length,
-                    progress_report_cb=progress_report_cb, md5_digest=raw)
+                if reader is None and raw is not None:
+                    payload = KnownBytesBody(data, raw, progress_report_cb)  # in memory, digest known: no reader at all
+                else:
+                    payload = BytesIOSegmentPayload(
+                        reader if reader is not None else BytesIO(data), segment_start=0, segment_length=content_length,
+                        progress_report_cb=progress_report_cb, md5_digest=raw)
             return await _upload_to_s3_url(url, payload, content_md5_b64=upload_hashes.md5_base64)
 
         result = await _blob_upload_with_fallback(resp.upload_urls.items, resp.blob_ids, send_single, content_length)

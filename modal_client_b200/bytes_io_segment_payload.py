@@ -16,7 +16,7 @@ import contextlib
 from collections.abc import Callable
 from typing import BinaryIO
 
-from aiohttp import Payload
+from aiohttp import BytesPayload, Payload
 from aiohttp.abc import AbstractStreamWriter
 
 from ._backend import get_context
@@ -165,3 +165,46 @@ class BytesIOSegmentPayload(Payload):
             self.num_bytes_read += len(chunk)
             await writer.write(chunk)
             self.progress_report_cb(advance=len(chunk))
+
+
+class KnownBytesBody:
+    """An in-memory blob on its way to a single-part PUT together with the MD5 the GPU batch already produced for it.
+    The map pump creates one per blobified input (10^5 per map), so this is a two-slot record; the aiohttp payload
+    is only built by ``as_payload()`` when a PUT really goes out.  The reference wraps every blob in a BytesIO and a
+    BytesIOSegmentPayload, whose ``write`` then hops to an executor thread per 16 MiB chunk to read memory that is
+    already in memory and to re-hash it (bytes_io_segment_payload.py:96-106)."""
+
+    __slots__ = ("data", "md5_raw", "progress_report_cb")
+
+    def __init__(self, data: bytes, md5_raw: bytes, progress_report_cb: Callable | None = None):
+        self.data, self.md5_raw, self.progress_report_cb = data, md5_raw, progress_report_cb
+
+    @property
+    def size(self) -> int:
+        return len(self.data)
+
+    def md5_checksum(self) -> _DigestKnown:
+        return _DigestKnown(self.md5_raw)
+
+    @contextlib.contextmanager
+    def reset_on_error(self, subtract_progress: bool = False):
+        try:
+            yield  # nothing to rewind: the body is immutable bytes, the digest is final
+        except Exception:
+            if self.progress_report_cb is not None:
+                self.progress_report_cb(advance=-len(self.data)) if subtract_progress else self.progress_report_cb(reset=True)
+            raise
+
+    def as_payload(self) -> "Payload":
+        body = _ReportingBytesPayload(self.data)
+        body.progress_report_cb = self.progress_report_cb
+        return body
+
+
+class _ReportingBytesPayload(BytesPayload):
+    progress_report_cb: Callable | None = None
+
+    async def write(self, writer: AbstractStreamWriter):
+        await super().write(writer)
+        if self.progress_report_cb is not None:
+            self.progress_report_cb(advance=len(self._value))

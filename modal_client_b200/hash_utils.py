@@ -100,9 +100,14 @@ class _UploadHashesRaw(UploadHashes):
     """UploadHashes that still knows the raw digests it was formatted from (rows of a GPU digest table), so the
     upload code does not have to decode the base64 again to compare ETags."""
 
-    __slots__ = ()
     md5_raw: bytes | None = None
     sha256_raw: bytes | None = None
+
+    def __init__(self, md5_base64: str, sha256_base64: str, md5_raw: bytes | None = None, sha256_raw: bytes | None = None):
+        self.md5_base64 = md5_base64
+        self.sha256_base64 = sha256_base64
+        self.md5_raw = md5_raw
+        self.sha256_raw = sha256_raw
 
     def md5_hex(self) -> str:
         return self.md5_raw.hex() if self.md5_raw is not None else super().md5_hex()
@@ -165,13 +170,10 @@ class _UploadHashesView(Sequence):
             i += self._n
         if not 0 <= i < self._n:
             raise IndexError(i)
-        out = _UploadHashesRaw(
-            md5_base64=self._md564[24 * i : 24 * i + 22] + "==" if self._md564 is not None else "",
-            sha256_base64=self._sha64[44 * i : 44 * i + 43] + "=")
-        out.sha256_raw = self._sha_bytes[32 * i : 32 * i + 32]
-        if self._md5_bytes is not None:
-            out.md5_raw = self._md5_bytes[16 * i : 16 * i + 16]
-        return out
+        if self._md564 is None:
+            return _UploadHashesRaw("", self._sha64[44 * i : 44 * i + 43] + "=", None, self._sha_bytes[32 * i : 32 * i + 32])
+        return _UploadHashesRaw(self._md564[24 * i : 24 * i + 22] + "==", self._sha64[44 * i : 44 * i + 43] + "=",
+                                self._md5_bytes[16 * i : 16 * i + 16], self._sha_bytes[32 * i : 32 * i + 32])
 
 
 def get_upload_hashes_many(payloads: Sequence[bytes], *, want_md5: bool = True, ctx=None) -> Sequence[UploadHashes]:

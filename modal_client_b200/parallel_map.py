@@ -31,9 +31,13 @@ from .function_utils import _blob_item, _function_fields, _inline_item, serializ
 
 MAP_INVOCATION_CHUNK_SIZE = 49  # inputs per FunctionPutInputs request (sync map)
 SPAWN_MAP_INVOCATION_CHUNK_SIZE = 512
-HASH_WINDOW_BYTES = 1 << 30  # payload bytes gathered into one GPU hash batch ...
+import os as _os
+
+# payload bytes gathered into one GPU hash batch (B200H_PUMP_WINDOW_BYTES) ...
+HASH_WINDOW_BYTES = int(_os.environ.get("B200H_PUMP_WINDOW_BYTES", 1 << 30))
 HASH_WINDOW_ITEMS = 65536  # ... and at most this many inputs (both: of what is ALREADY queued)
-HASH_WINDOWS_IN_FLIGHT = 2  # windows being hashed at the same time (one library context each)
+# windows being hashed at the same time, one library context each (B200H_PUMP_WINDOWS_IN_FLIGHT)
+HASH_WINDOWS_IN_FLIGHT = int(_os.environ.get("B200H_PUMP_WINDOWS_IN_FLIGHT", 2))
 PUMP_INPUTS_MAX_RETRY_DELAY = 15.0  # reference :67 (RESOURCE_EXHAUSTED back-off ceiling of the pumper)
 
 _END = object()
@@ -123,6 +127,14 @@ class _WindowedInputPipeline:
             await out.put(_END)
 
     # ---- stage 3: upload, emit in order ---------------------------------------------------------------------
+    async def run(self, emit: Callable[[Any], Any]) -> None:
+        """Drive the pipeline to the end of the input; ``emit(item)`` receives every wire item in input order and may
+        return an awaitable (a full bounded queue) that is then awaited."""
+        async for item in self.items():
+            pending = emit(item)
+            if pending is not None:
+                await pending
+
     async def items(self):
         handoff: asyncio.Queue = asyncio.Queue(maxsize=HASH_WINDOWS_IN_FLIGHT)
         producer = asyncio.ensure_future(self._collect_and_hash(handoff))
@@ -183,8 +195,9 @@ class InputPreprocessor:
                                       on_created=self._created, serializer=self.serializer)
         if self.keep_digest_tables:
             pipe.digest_tables = self.digest_tables
-        async for item in pipe.items():
-            await self.processed_input_queue.put(item)
+        q = self.processed_input_queue
+        # an unbounded queue (the reference's) never blocks: skip the coroutine round trip per item
+        await pipe.run(lambda item: q.put_nowait(item) if not q.full() else q.put(item))
         self.hash_batches = pipe.windows_hashed
         await self.processed_input_queue.put(None)  # end-of-queue marker for the pumper
         self.done_callback()
