@@ -268,6 +268,7 @@ def run_map_pump(payloads, stub) -> float:
         await asyncio.gather(drive(pre.drain_input_generator()), drive(pump.pump_inputs()))
         dt = time.perf_counter() - t0
         assert pump.inputs_sent == len(payloads)
+        run_map_pump.last_stats = {k: round(v, 4) for k, v in pre.stats.items()}
         return dt, pre.hash_batches, pre.digest_tables
 
     return asyncio.run(main())
@@ -519,7 +520,9 @@ def run_gpu(args) -> None:
                            + (" + sharding.all_gather_table (NCCL)" if world > 1 else ""),
                     "hash_batches_per_step": pump_batches,
                     "window_bytes": parallel_map.HASH_WINDOW_BYTES, "windows_in_flight": parallel_map.HASH_WINDOWS_IN_FLIGHT,
-                    "gpu_launches": int(pump_launches)},
+                    "gpu_launches": int(pump_launches),
+                    "stage_seconds_last_step": getattr(run_map_pump, "last_stats", None),
+                    "seconds_last_step": round(_dt, 4)},
             "e2e_pinned": {"value": round(pinned_value, 3), "unit": "GiB/s", "steps": e2e_steps,
                            "api": "batch.hash_table_host on page-locked host memory (one call, 100 000 messages)"
                                   + (" + sharding.all_gather_table (NCCL)" if world > 1 else "")},

@@ -81,48 +81,54 @@ async def bounded_map_ordered(items, fn, concurrency: int):
     yielding the results IN INPUT ORDER as soon as each one and all its predecessors are finished -- the streaming
     behaviour of the reference's ``async_map_ordered`` (py/modal/_utils/async_utils.py:1200-1227) for an input that
     is already materialised.  At most ``2 * concurrency`` finished results wait for a slow predecessor (the
-    reference's buffer bound).  The first failure cancels the rest and re-raises."""
+    reference's buffer bound).  The first failure cancels the rest and re-raises.  (Written for ~1 us of overhead per
+    item: the map pump pushes 10^5 inputs through it.)"""
     items = list(items)
     n = len(items)
     if n == 0:
         return
-    results: dict[int, object] = {}
-    state = {"next_in": 0, "next_out": 0, "error": None}
+    pending = object()
+    results: list = [pending] * n
+    next_in = 0
+    next_out = 0
+    error = None
     wake_consumer = asyncio.Event()
     wake_workers = asyncio.Event()
     window = max(1, 2 * concurrency)
 
     async def worker():
+        nonlocal next_in, error
         while True:
-            i = state["next_in"]
-            if i >= n or state["error"] is not None:
+            i = next_in
+            if i >= n or error is not None:
                 return
-            if i - state["next_out"] >= window:  # too far ahead of the slowest predecessor: wait for the consumer
+            if i - next_out >= window:  # too far ahead of the slowest predecessor: wait for the consumer
                 wake_workers.clear()
                 await wake_workers.wait()
                 continue
-            state["next_in"] = i + 1
+            next_in = i + 1
             try:
                 results[i] = await fn(items[i])
             except BaseException as exc:  # noqa: BLE001 - handed to the consumer
-                if state["error"] is None:
-                    state["error"] = exc
+                if error is None:
+                    error = exc
                 wake_consumer.set()
                 return
-            if i == state["next_out"]:
+            if i == next_out:
                 wake_consumer.set()
 
     workers = [asyncio.ensure_future(worker()) for _ in range(max(1, min(concurrency, n)))]
     try:
-        while state["next_out"] < n:
-            j = state["next_out"]
-            if j in results:  # finished results are handed out even if a later item has failed meanwhile
-                state["next_out"] = j + 1
+        while next_out < n:
+            r = results[next_out]
+            if r is not pending:  # finished results are handed out even if a later item has failed meanwhile
+                results[next_out] = None
+                next_out += 1
                 wake_workers.set()
-                yield results.pop(j)
+                yield r
                 continue
-            if state["error"] is not None:
-                raise state["error"]
+            if error is not None:
+                raise error
             wake_consumer.clear()
             await wake_consumer.wait()
     finally:

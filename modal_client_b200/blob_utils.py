@@ -316,6 +316,7 @@ async def _blob_upload(
     stub,
     progress_report_cb: Callable | None = None,
     byte_budget: _ByteBudget | None = None,
+    _blob_create_response=None,
 ) -> tuple[str, bool, int]:
     """BlobCreate with the precomputed digests, then a single PUT or a multipart upload (reference :271-335).
     The map pump calls this once per blobified input, 10^5 times per map: a ``bytes`` payload is not wrapped in a
@@ -324,13 +325,15 @@ async def _blob_upload(
         reader, content_length = None, len(data)
     else:
         reader, content_length = data, get_content_length(data)
-    resp = await stub.BlobCreate(
-        BlobCreateRequest(
-            content_md5=upload_hashes.md5_base64,
-            content_sha256_base64=upload_hashes.sha256_base64,
-            content_length=content_length,
+    resp = _blob_create_response  # set when _blob_upload_bytes already made the request
+    if resp is None:
+        resp = await stub.BlobCreate(
+            BlobCreateRequest(
+                content_md5=upload_hashes.md5_base64,
+                content_sha256_base64=upload_hashes.sha256_base64,
+                content_length=content_length,
+            )
         )
-    )
     if resp.WhichOneof("upload_types_oneof") == "multiparts":
         if reader is None:
             reader = BytesIO(data)
@@ -370,6 +373,39 @@ async def _blob_upload(
     if progress_report_cb:
         progress_report_cb(complete=True)
     return result
+
+
+async def _blob_upload_bytes(upload_hashes: UploadHashes, data: bytes, stub) -> tuple[str, bool, int]:
+    """``_blob_upload`` for the map pump's case -- an in-memory payload whose digests came out of a GPU batch --
+    with the single-PUT branch and the provider fallback written out flat (same BlobCreate request, same fallback
+    order, same r2 bookkeeping as ``_blob_upload`` / ``_blob_upload_with_fallback``): 10^5 of these run per map on the
+    event-loop thread, and every coroutine frame and closure per input is paid there.  Anything else (multipart
+    answer, digest unknown) goes through the general function."""
+    md5_raw = getattr(upload_hashes, "md5_raw", None)
+    content_length = len(data)
+    md5_b64 = upload_hashes.md5_base64
+    resp = await stub.BlobCreate(BlobCreateRequest(content_md5=md5_b64, content_sha256_base64=upload_hashes.sha256_base64,
+                                                   content_length=content_length))
+    if md5_raw is None or resp.WhichOneof("upload_types_oneof") != "upload_urls":
+        return await _blob_upload(upload_hashes, data, stub, _blob_create_response=resp)
+    body = KnownBytesBody(data, md5_raw)
+    urls, blob_ids = resp.upload_urls.items, resp.blob_ids
+    r2_failed, last = False, len(urls) - 1
+    for idx, url in enumerate(urls):
+        blob_id = blob_ids[idx]
+        is_r2 = blob_id.endswith(":r2")
+        try:
+            if is_r2:
+                t0 = time.monotonic_ns()
+                await _upload_to_s3_url(url, body, content_md5_b64=md5_b64)
+                return blob_id, r2_failed, (content_length * 1_000_000_000) // max(time.monotonic_ns() - t0, 1)
+            await _upload_to_s3_url(url, body, content_md5_b64=md5_b64)
+            return blob_id, r2_failed, 0
+        except Exception:
+            r2_failed = r2_failed or is_r2
+            if idx == last:
+                raise
+    raise ExecutionError("Failed to upload blob")
 
 
 def _is_real_md5(h: UploadHashes) -> bool:

@@ -21,13 +21,14 @@ The retry / output-polling state machine of the reference (:1320-1644) is contro
 from __future__ import annotations
 
 import asyncio
+import time
 from collections.abc import Callable
 from typing import Any
 
 from . import _backend, _wire, blob_utils, hash_utils
 from ._logging import logger
 from .async_utils import bounded_map_ordered
-from .function_utils import _blob_item, _function_fields, _inline_item, serialize_data_format, should_upload
+from .function_utils import _blob_item, _function_fields, _inline_item, serialize_data_format
 
 MAP_INVOCATION_CHUNK_SIZE = 49  # inputs per FunctionPutInputs request (sync map)
 SPAWN_MAP_INVOCATION_CHUNK_SIZE = 512
@@ -71,17 +72,23 @@ class _WindowedInputPipeline:
         self.on_created = on_created or (lambda n: None)
         self.make_item = make_item or (lambda item: item)
         self.windows_hashed = 0
+        # where the time went (seconds): collecting+serializing, waiting for a free context, inside the GPU hash calls
+        # (summed over worker threads), the upload stage waiting for a window's digests
+        self.stats = {"collect_s": 0.0, "wait_context_s": 0.0, "hash_call_s": 0.0, "wait_hash_s": 0.0}
         self.digest_tables: list | None = None  # set to [] to keep every window's (sha[n,32], md5[n,16]) arrays
 
     # ---- stage 1: collect ----------------------------------------------------------------------------------
     def _take(self, win: _Window, argskwargs) -> int:
         payload = self.serializer(argskwargs) if self.serializer else serialize_data_format(argskwargs, self.data_format)
-        if should_upload(len(payload), self.max_bytes, self.invocation_type):
+        nbytes = len(payload)
+        # should_upload(), written out (strictly greater than the function's limit; the 8 KiB limit for async calls)
+        if nbytes > self.max_bytes or (nbytes > blob_utils.MAX_ASYNC_OBJECT_SIZE_BYTES
+                                       and self.invocation_type == _wire.FUNCTION_CALL_INVOCATION_TYPE_ASYNC):
             win.big.append(len(win.payloads))
         win.payloads.append(payload)
         self.next_idx += 1
         self.on_created(self.next_idx - self.first_idx)
-        return len(payload)
+        return nbytes
 
     async def _next_window(self) -> tuple[_Window | None, bool]:
         """Block for one raw input, then take what is already queued, up to the byte / item budget."""
@@ -111,14 +118,25 @@ class _WindowedInputPipeline:
             free.put_nowait(c)
         finished = False
         try:
+            def hash_window(c, payloads):
+                t = time.perf_counter()
+                try:
+                    return hash_utils.get_upload_hashes_many(payloads, ctx=c)
+                finally:
+                    self.stats["hash_call_s"] += time.perf_counter() - t
+
             while not finished:
+                t0 = time.perf_counter()
                 win, finished = await self._next_window()
+                self.stats["collect_s"] += time.perf_counter() - t0
                 if win is None:
                     break
                 if win.big:
+                    t0 = time.perf_counter()
                     ctx = await free.get()  # at most one batch per context at a time
+                    self.stats["wait_context_s"] += time.perf_counter() - t0
                     big_payloads = [win.payloads[i] for i in win.big]
-                    fut = loop.run_in_executor(None, lambda c=ctx, p=big_payloads: hash_utils.get_upload_hashes_many(p, ctx=c))
+                    fut = loop.run_in_executor(None, hash_window, ctx, big_payloads)
                     fut.add_done_callback(lambda _f, c=ctx: free.put_nowait(c))
                     win.hashes = fut
                     self.windows_hashed += 1
@@ -143,7 +161,9 @@ class _WindowedInputPipeline:
                 win = await handoff.get()
                 if win is _END:
                     break
+                t0 = time.perf_counter()
                 hashes = await win.hashes if win.hashes is not None else ()
+                self.stats["wait_hash_s"] += time.perf_counter() - t0
                 if self.digest_tables is not None and win.hashes is not None:
                     self.digest_tables.append((hashes._sha, hashes._md5))
                 big_pos = {pos: k for k, pos in enumerate(win.big)}
@@ -154,7 +174,7 @@ class _WindowedInputPipeline:
                     k = big_pos.get(pos)
                     if k is None:
                         return _inline_item(win.first_idx + pos, payload, self.data_format, self.method_name)
-                    upload = await blob_utils._blob_upload(hashes[k], payload, self.stub)
+                    upload = await blob_utils._blob_upload_bytes(hashes[k], payload, self.stub)
                     return _blob_item(win.first_idx + pos, upload, self.data_format, self.method_name)
 
                 async for item in bounded_map_ordered(range(len(win.payloads)), build, blob_utils.BLOB_MAX_PARALLELISM):
@@ -183,6 +203,7 @@ class InputPreprocessor:
         self.done_callback = done_callback
         self.serializer = serializer  # None: the negotiated payload format's serializer (pickle / CBOR)
         self.hash_batches = 0
+        self.stats: dict = {}
         self.keep_digest_tables = False  # True: ``digest_tables`` collects each window's (sha, md5) numpy tables
         self.digest_tables: list = []
 
@@ -199,6 +220,7 @@ class InputPreprocessor:
         # an unbounded queue (the reference's) never blocks: skip the coroutine round trip per item
         await pipe.run(lambda item: q.put_nowait(item) if not q.full() else q.put(item))
         self.hash_batches = pipe.windows_hashed
+        self.stats = pipe.stats
         await self.processed_input_queue.put(None)  # end-of-queue marker for the pumper
         self.done_callback()
         yield
@@ -304,8 +326,6 @@ class InputPlanePreprocessor:
         self.update_counters(created_delta=delta)
 
     async def drain_input_generator(self):
-        import time
-
         pipe = _WindowedInputPipeline(
             self.raw_input_queue, self.client.stub, self.function, first_idx=1,  # 1-indexed map call idx (:708)
             on_created=self._created, serializer=self.serializer,
