@@ -284,6 +284,8 @@ def run_gpu(args) -> None:
     rank, world, local_rank = env_rank()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa_bound = sharding.bind_process_to_gpu_node(local_rank)  # one process per GPU: stay next to it
     if world > 1:
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)  # the gather slips in between hash kernels
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
@@ -459,6 +461,7 @@ def run_gpu(args) -> None:
     if gather_ok is not None:
         parity += "; all-gathered slice == own table: %s" % ("exact" if gather_ok else "MISMATCH")
     if rank == 0 and world == 1:
+        os.sched_setaffinity(0, all_cpus)  # the reference's thread pool gets every host core again
         sample_n = min(int(os.environ.get("B200H_CPU_SAMPLE", 16384)), N_MSG)
         sample = payloads[:sample_n]
         from concurrent.futures import ThreadPoolExecutor
@@ -503,7 +506,7 @@ def run_gpu(args) -> None:
                        "l2": "inputs (24.4 GiB/GPU) larger than L2, no flush needed", "parallelism": f"shard{world}",
                        "collective": ("nccl all_gather of ONE packed 48-B-row digest table per step on a side stream, "
                                       "double buffered (gather k overlaps hash k+1)") if world > 1 else "none",
-                       "host_syncs_in_timed_region": int(plan_syncs)},
+                       "host_syncs_in_timed_region": int(plan_syncs), "process_bound_to_gpu_numa_node": bool(numa_bound)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "lane_hash_kernel<sha256,md5>",

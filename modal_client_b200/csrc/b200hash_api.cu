@@ -9,6 +9,8 @@
 
 #include <fcntl.h>
 #include <immintrin.h>
+#include <pthread.h>
+#include <sched.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -18,6 +20,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cctype>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -148,6 +151,11 @@ struct b200h_ctx {
     uint64_t prof_n = 0;
     int pack_threads = 1;
     int io_threads = 1;
+    // CPUs of the NUMA node the GPU hangs off (empty set: unknown / single node / B200H_NUMA=0).  The packer and
+    // reader threads are pinned there: the staging ring lives in that node's memory and the DMA engine reads it from
+    // there, so a packer on the other socket would push every byte across the socket interconnect twice.
+    cpu_set_t node_cpus;
+    bool node_cpus_valid = false;
 };
 
 struct b200h_stream {
@@ -170,6 +178,63 @@ struct b200h_stream {
 namespace {
 
 void stream_res_destroy(b200h_ctx::StreamBuf& r);  // defined with the streaming entry points
+
+// "0-31,64-95" -> cpu_set_t
+bool parse_cpulist(const char* s, cpu_set_t* out) {
+    CPU_ZERO(out);
+    int n = 0;
+    while (*s && *s != '\n') {
+        char* end = nullptr;
+        long a = strtol(s, &end, 10);
+        if (end == s) return false;
+        long b = a;
+        if (*end == '-') {
+            s = end + 1;
+            b = strtol(s, &end, 10);
+            if (end == s) return false;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
+            CPU_SET((int)c, out);
+            ++n;
+        }
+        s = *end == ',' ? end + 1 : end;
+    }
+    return n > 0;
+}
+
+// CPUs local to CUDA device `device` (sysfs: the PCI function's numa_node -> that node's cpulist)
+bool gpu_node_cpus(int device, cpu_set_t* out) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[128], buf[4096];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return false;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return false;
+    const bool got = fgets(buf, sizeof buf, f) != nullptr;
+    fclose(f);
+    if (!got || !parse_cpulist(buf, out)) return false;
+    // keep only CPUs this process may run on (cgroup / taskset); if none is left, give up
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0) {
+        cpu_set_t both;
+        CPU_AND(&both, out, &allowed);
+        if (CPU_COUNT(&both) == 0) return false;
+        // a process already confined to a subset keeps its own mask
+        *out = both;
+    }
+    return true;
+}
 
 int fail(b200h_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -440,7 +505,7 @@ void pack_range(const Source& src, const uint64_t* len, const uint64_t* doff, ui
 }
 
 void pack_parallel(int threads, const Source& src, const uint64_t* len, const uint64_t* doff, uint64_t i0, uint64_t i1,
-                   uint64_t lo, uint64_t hi, uint8_t* dst) {
+                   uint64_t lo, uint64_t hi, uint8_t* dst, const cpu_set_t* cpus = nullptr) {
     const uint64_t bytes = hi - lo;
     // memory sources: one thread per >= 4 MiB; file sources: syscalls dominate small files, so also split by count
     uint64_t want = bytes / (4u << 20);
@@ -455,6 +520,7 @@ void pack_parallel(int threads, const Source& src, const uint64_t* len, const ui
     for (int k = 0; k < t; ++k) {
         const uint64_t a = lo + bytes * k / t, b = lo + bytes * (k + 1) / t;
         th.emplace_back([=, &src] { pack_range(src, len, doff, i0, i1, a, b, dst + (a - lo)); });
+        if (cpus) pthread_setaffinity_np(th.back().native_handle(), sizeof(cpu_set_t), cpus);  // best effort
     }
     for (auto& x : th) x.join();
 }
@@ -599,12 +665,13 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
             for (uint64_t lo = 0; lo < w.bytes; lo += ctx->pin_cap) {
                 const uint64_t hi = std::min<uint64_t>(w.bytes, lo + ctx->pin_cap);
                 if (pin_used[pin_slot]) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_pin[pin_slot]));
+                const cpu_set_t* cpus = ctx->node_cpus_valid ? &ctx->node_cpus : nullptr;
                 if (w.seg)
                     pack_parallel(paths ? ctx->io_threads : ctx->pack_threads, seg_src, &seg_len1, &seg_doff1, 0, 1, lo, hi,
-                                  ctx->pin[pin_slot]);
+                                  ctx->pin[pin_slot], cpus);
                 else
                     pack_parallel(paths ? ctx->io_threads : ctx->pack_threads, src, len, doff, w.i0, w.i1, lo, hi,
-                                  ctx->pin[pin_slot]);
+                                  ctx->pin[pin_slot], cpus);
                 if (io_errno.load()) {
                     const int e = io_errno.load();
                     CU_TRY(ctx, cudaDeviceSynchronize());
@@ -830,9 +897,20 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
     ctx->dwave_want = std::max<size_t>((device_bytes / 2) & ~size_t(255), 1 << 20);
     for (int s = 0; s < 2; ++s) CU_INIT(cudaHostAlloc(&ctx->pin[s], ctx->pin_cap, cudaHostAllocDefault));
     unsigned hc = std::thread::hardware_concurrency();
-    ctx->pack_threads = (int)std::min(16u, std::max(1u, hc / 2));  // measured best on 2x Xeon 8562Y+ (8..64 tried)
+    // One process per GPU shares the host with its siblings: with LOCAL_WORLD_SIZE ranks (torchrun) each keeping two
+    // batches in flight, 16 packers per context oversubscribe the cores (8 ranks x 2 x 16 = 256 threads on 128 CPUs)
+    unsigned share = hc;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+        const int lw = atoi(e);
+        if (lw > 1) share = std::max(4u, hc / (unsigned)lw);
+    }
+    ctx->pack_threads = (int)std::min(16u, std::max(1u, share / 2));  // measured best on 2x Xeon 8562Y+ (8..64 tried)
+    {
+        const char* e = getenv("B200H_NUMA");
+        if (!(e && atoi(e) == 0)) ctx->node_cpus_valid = gpu_node_cpus(device, &ctx->node_cpus);
+    }
     if (const char* e = getenv("B200H_PACK_THREADS")) ctx->pack_threads = std::max(1, atoi(e));
-    ctx->io_threads = (int)std::min(16u, std::max(1u, hc));  // measured: 16 > 32 > 64 > 128 (kernel-side contention)
+    ctx->io_threads = (int)std::min(16u, std::max(1u, share));  // measured: 16 > 32 > 64 > 128 (kernel-side contention)
     if (const char* e = getenv("B200H_IO_THREADS")) ctx->io_threads = std::max(1, atoi(e));
     if (const char* e = getenv("B200H_VERIFY_PLAN")) ctx->verify_plan = atoi(e) != 0;
     if (const char* e = getenv("B200H_COMBINE")) ctx->combine_enabled = atoi(e) != 0;

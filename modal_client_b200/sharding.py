@@ -14,6 +14,48 @@ from ._lib import MD5, SHA256, TRIM_ZEROS
 from .batch import DigestTable
 
 
+def gpu_node_cpus(device: int) -> set[int] | None:
+    """CPUs of the NUMA node CUDA device ``device`` hangs off (sysfs), or None when that cannot be told."""
+    import os
+
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            text = f.read().strip()
+    except Exception:
+        return None
+    cpus: set[int] = set()
+    for part in text.split(","):
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    cpus &= os.sched_getaffinity(0)
+    return cpus or None
+
+
+def bind_process_to_gpu_node(device: int) -> bool:
+    """One process per GPU: run this process (and every thread it starts later) on the CPUs next to its GPU, so that
+    the payloads it allocates, the pinned staging ring and the packer threads all sit in the memory the GPU's DMA
+    engine reads from.  torchrun does not do this; without it 8 ranks packing pageable payloads push most bytes
+    across the socket interconnect (measured: map-pump e2e 8 GPUs 64 -> see profiles/).  Returns whether it bound."""
+    import os
+
+    cpus = gpu_node_cpus(device)
+    if not cpus:
+        return False
+    try:
+        os.sched_setaffinity(0, cpus)
+        return True
+    except OSError:
+        return False
+
+
 def shard_assignment(lengths, world: int) -> list[np.ndarray]:
     """Byte-balanced partition of message indices over ``world`` ranks: sort by length (longest first) and
     deal in boustrophedon order (0..w-1, w-1..0, ...), the vectorisable cousin of LPT list scheduling.

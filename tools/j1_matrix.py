@@ -36,6 +36,7 @@ WITH_CPU = "cpu" in which
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
+    sharding.bind_process_to_gpu_node(local)
     dist.init_process_group("nccl", device_id=dev)
 ctx = _lib.Context(local, pinned_bytes=512 << 20, device_bytes=8 << 30)
 st = torch.cuda.Stream(device=dev)
