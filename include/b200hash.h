@@ -31,6 +31,9 @@ extern "C" {
 #define B200H_SHA256 1u     /* compute SHA-256 */
 #define B200H_MD5 2u        /* compute MD5 */
 #define B200H_TRIM_ZEROS 4u /* hash the prefix up to the last non-zero byte (volumefs2 blocks) */
+#define B200H_HEX_OUT 32u /* the digest outputs receive lowercase ASCII hex (64 chars per SHA-256 row, 32 per MD5
+                             row; buffers twice as wide) formatted on the device: the column MountFile.sha256_hex /
+                             FileUploadSpec.md5_hex carry (modal_proto/api.proto:2582-2587), straight from the table */
 #define B200H_NO_OUTLIERS 16u /* keep every message on the lane kernel (no outlier routing): with it
                                  b200h_hash_batch_device never reads anything back, i.e. only enqueues */
 

@@ -21,6 +21,7 @@ CSRC = os.path.join(_PKG, "csrc")
 SHA256 = 1
 MD5 = 2
 TRIM_ZEROS = 4
+HEX_OUT = 32  # digest outputs as lowercase ASCII hex rows (64 / 32 chars), formatted on the device
 NO_OUTLIERS = 16  # keep every message on the lane kernel: device batches then only enqueue (include/b200hash.h)
 
 #: every symbol include/b200hash.h declares (tests check the .so exports all of them)
@@ -240,8 +241,9 @@ class Context:
         else:
             keep = np.frombuffer(base, dtype=np.uint8)
             bp = ctypes.c_void_p(keep.ctypes.data) if keep.size else ctypes.c_void_p(off.ctypes.data)
-        sha = np.empty((n, 32), np.uint8) if (flags & SHA256 and not out_sha) else None
-        md5 = np.empty((n, 16), np.uint8) if (flags & MD5 and not out_md5) else None
+        wide = 2 if flags & HEX_OUT else 1  # hex rows are twice as wide
+        sha = np.empty((n, 32 * wide), np.uint8) if (flags & SHA256 and not out_sha) else None
+        md5 = np.empty((n, 16 * wide), np.uint8) if (flags & MD5 and not out_md5) else None
         trimmed = None if out_trimmed else np.empty(n, np.uint64)
         rc = self._L.b200h_hash_batch_host(self._h, bp, _np_ptr(off), _np_ptr(ln), n, flags,
                                            ctypes.c_void_p(out_sha) if out_sha else _np_ptr(sha),
@@ -323,8 +325,9 @@ class Context:
         sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
         n = len(keep)
         rows = n if part_len == 0 else int(((sizes + np.uint64(part_len - 1)) // np.uint64(part_len)).sum())
-        sha = np.empty((rows, 32), np.uint8) if flags & SHA256 else None
-        md5 = np.empty((rows, 16), np.uint8) if flags & MD5 else None
+        wide = 2 if flags & HEX_OUT else 1
+        sha = np.empty((rows, 32 * wide), np.uint8) if flags & SHA256 else None
+        md5 = np.empty((rows, 16 * wide), np.uint8) if flags & MD5 else None
         trimmed = np.empty(rows, np.uint64)
         rc = self._L.b200h_hash_files(self._h, arr, n, _np_ptr(sizes), part_len, flags, _np_ptr(sha), _np_ptr(md5),
                                       _np_ptr(trimmed))

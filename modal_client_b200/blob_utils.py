@@ -604,23 +604,53 @@ def get_file_upload_specs(
     use_blob = sizes >= LARGE_FILE_LIMIT
     want_md5 = ~(use_blob & (sizes > MULTIPART_UPLOAD_THRESHOLD))
     cacheable = ~use_blob & (sizes < SMALL_FILE_INLINE_LIMIT)
-    # one fused SHA-256+MD5 batch for the files that need both, a SHA-only batch for the > 1 GiB class
-    sha_all = np.empty((n, 32), np.uint8)
-    md5_all = np.zeros((n, 16), np.uint8)
-    both = np.flatnonzero(want_md5)
-    sha_only = np.flatnonzero(~want_md5)
-    if both.size:
-        sha, md5, _ = ctx.hash_files([paths[i] for i in both] if both.size != n else paths, sizes[both], 0,
-                                     _lib.SHA256 | _lib.MD5)
-        sha_all[both], md5_all[both] = sha, md5
-    if sha_only.size:
-        sha, _, _ = ctx.hash_files([paths[i] for i in sha_only], sizes[sha_only], 0, _lib.SHA256)
-        sha_all[sha_only] = sha
-    sha_hex, md5_hex = sha_all.tobytes().hex(), md5_all.tobytes().hex()  # one conversion, sliced per file below
     if cache_small_content is None:
         cache_small_content = n <= 4096
+    # Files whose content is cached in the spec (< 256 KiB, like the reference's "read once" class) are read ONCE, here,
+    # and those very bytes are hashed -- the digest can never disagree with spec.content, whatever happens to the
+    # file meanwhile.  Everything else is read by the library's native reader.
+    contents: dict[int, bytes] = {}
+    if cache_small_content:
+        for i in np.flatnonzero(cacheable).tolist():
+            with open(files[i][0], "rb") as f:
+                contents[i] = f.read()
+        if contents:
+            idx = np.fromiter(contents.keys(), dtype=np.int64, count=len(contents))
+            sizes[idx] = [len(c) for c in contents.values()]
+    from_memory = np.zeros(n, bool)
+    if contents:
+        from_memory[list(contents.keys())] = True
+    # one fused SHA-256+MD5 batch for the files that need both, a SHA-only batch for the > 1 GiB class.  The digest
+    # columns come back as the hex text the wire rows carry (FileUploadSpec / MountFile.sha256_hex), formatted on the
+    # device from the digest table (B200H_HEX_OUT) -- no per-row conversion on the host.
+    HEX = _lib.HEX_OUT
+    sha_all = np.empty((n, 64), np.uint8)
+    md5_all = np.full((n, 32), ord("0"), np.uint8)
+    if contents:
+        idx = np.flatnonzero(from_memory)
+        sha, md5, _ = ctx.hash_buffers([contents[i] for i in idx.tolist()], _lib.SHA256 | _lib.MD5 | HEX)
+        sha_all[idx], md5_all[idx] = sha, md5
+    both = np.flatnonzero(want_md5 & ~from_memory)
+    sha_only = np.flatnonzero(~want_md5 & ~from_memory)
+    if both.size:
+        sha, md5, _ = ctx.hash_files([paths[i] for i in both] if both.size != n else paths, sizes[both], 0,
+                                     _lib.SHA256 | _lib.MD5 | HEX)
+        sha_all[both], md5_all[both] = sha, md5
+    if sha_only.size:
+        sha, _, _ = ctx.hash_files([paths[i] for i in sha_only], sizes[sha_only], 0, _lib.SHA256 | HEX)
+        sha_all[sha_only] = sha
+    # A file that GREW between the stat and the read was hashed as its old prefix (a file that shrank fails the read):
+    # stat again and redo the few that changed one at a time, the reference's way (one open, size and bytes together).
+    redo: dict[int, FileUploadSpec] = {}
+    streamed = np.flatnonzero(~from_memory)
+    if streamed.size:
+        sizes_after, _ = ctx.stat_files([paths[i] for i in streamed] if streamed.size != n else paths)
+        for i in streamed[sizes_after != sizes[streamed]].tolist():
+            filename, mount_filename, mode = files[i]
+            redo[i] = get_file_upload_spec_from_path(Path(filename), PurePosixPath(mount_filename), mode)
+    sha_hex, md5_hex = sha_all.tobytes().decode("ascii"), md5_all.tobytes().decode("ascii")  # sliced per file below
     sizes_l, modes_l = sizes.tolist(), modes.tolist()
-    use_blob_l, want_md5_l, cache_l = use_blob.tolist(), want_md5.tolist(), cacheable.tolist()
+    use_blob_l, want_md5_l = use_blob.tolist(), want_md5.tolist()
     # The per-file Python work below is what is left of a million-file tree once hashing takes a fraction of a second,
     # so it is kept to positional construction and precomputed columns (~2.5 us per file).
     partial, spec_cls, placeholder = functools.partial, FileUploadSpec, _MD5_PLACEHOLDER
@@ -630,21 +660,21 @@ def get_file_upload_specs(
     gc_was_on = gc.isenabled()
     gc.disable()
     try:
-        _build_specs(files, append, spec_cls, partial, placeholder, cache_small_content, cache_l, use_blob_l, want_md5_l,
+        _build_specs(files, append, spec_cls, partial, placeholder, contents, use_blob_l, want_md5_l,
                      sha_hex, md5_hex, modes_l, sizes_l)
     finally:
         if gc_was_on:
             gc.enable()
+    for i, spec in redo.items():
+        specs[i] = spec
     return specs
 
 
-def _build_specs(files, append, spec_cls, partial, placeholder, cache_small_content, cache_l, use_blob_l, want_md5_l,
+def _build_specs(files, append, spec_cls, partial, placeholder, contents, use_blob_l, want_md5_l,
                  sha_hex, md5_hex, modes_l, sizes_l) -> None:
+    get_content = contents.get
     for i, (filename, mount_filename, mode) in enumerate(files):
-        content = None
-        if cache_small_content and cache_l[i]:
-            with open(filename, "rb") as f:
-                content = f.read()
+        content = get_content(i)  # the bytes that were hashed (cached class only)
         append(
             spec_cls(
                 partial(open, filename, "rb"),                                        # source

@@ -141,7 +141,7 @@ struct b200h_ctx {
     uint8_t* dwave[2] = {nullptr, nullptr};
     size_t dwave_cap = 0;  // per slot
     size_t dwave_want = 0;
-    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small, d_states, d_dedupe, d_keys, d_trimctl;
+    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small, d_states, d_dedupe, d_keys, d_trimctl, d_hex;
     uint64_t* h_meta = nullptr;  // pinned: offsets then lengths
     size_t h_meta_cap = 0;       // in uint64 elements
     uint64_t launches = 0;
@@ -732,15 +732,32 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
     }
     // The output arrays may live in host OR device memory (cudaMemcpyDefault): a caller that goes on to all-gather
     // the table over NCCL passes device buffers and the digests never visit the host.
-    if (sha_out && d_sha) CU_TRY(ctx, cudaMemcpyAsync(sha_out, d_sha, n * 32, cudaMemcpyDefault, ctx->s_comp));
-    if (md5_out && d_md5) CU_TRY(ctx, cudaMemcpyAsync(md5_out, d_md5, n * 16, cudaMemcpyDefault, ctx->s_comp));
+    if (flags & B200H_HEX_OUT) {
+        // the digest columns leave the device as lowercase ASCII hex (64 / 32 characters per row)
+        const bool want_sha = sha_out && d_sha, want_md5 = md5_out && d_md5;
+        if (int rc = ensure_dev(ctx, ctx->d_hex, n * 96 + 64)) return rc;
+        uint8_t* hex_sha = (uint8_t*)ctx->d_hex.p;
+        uint8_t* hex_md5 = hex_sha + n * 64;
+        if (want_sha) {
+            ctx->launches += launch_hex_rows(d_sha, n * 32, hex_sha, ctx->s_comp);
+            CU_TRY(ctx, cudaMemcpyAsync(sha_out, hex_sha, n * 64, cudaMemcpyDefault, ctx->s_comp));
+        }
+        if (want_md5) {
+            ctx->launches += launch_hex_rows(d_md5, n * 16, hex_md5, ctx->s_comp);
+            CU_TRY(ctx, cudaMemcpyAsync(md5_out, hex_md5, n * 32, cudaMemcpyDefault, ctx->s_comp));
+        }
+        CU_TRY(ctx, cudaGetLastError());
+    } else {
+        if (sha_out && d_sha) CU_TRY(ctx, cudaMemcpyAsync(sha_out, d_sha, n * 32, cudaMemcpyDefault, ctx->s_comp));
+        if (md5_out && d_md5) CU_TRY(ctx, cudaMemcpyAsync(md5_out, d_md5, n * 16, cudaMemcpyDefault, ctx->s_comp));
+    }
     if (trim_out) CU_TRY(ctx, cudaMemcpyAsync(trim_out, d_trim, n * sizeof(uint64_t), cudaMemcpyDefault, ctx->s_comp));
     if (etag_out) CU_TRY(ctx, cudaMemcpyAsync(etag_out, d_etag, 16, cudaMemcpyDefault, ctx->s_comp));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->s_comp));
     return 0;
 }
 
-constexpr uint32_t kPublicFlags = 7u | B200H_NO_OUTLIERS;
+constexpr uint32_t kPublicFlags = 7u | B200H_NO_OUTLIERS | B200H_HEX_OUT;
 
 // A small request from one of possibly many concurrent callers: merge it with whatever else arrives while the context
 // is busy, run ONE batch, hand every caller its rows.  (See Combiner.)
@@ -932,7 +949,7 @@ void b200h_destroy(b200h_ctx* ctx) {
         cudaEventDestroy(pr.second);
     }
     for (DevBuf* b : {&ctx->d_off, &ctx->d_len, &ctx->d_order, &ctx->d_trim, &ctx->d_sha, &ctx->d_md5, &ctx->d_scratch,
-                      &ctx->d_small, &ctx->d_states, &ctx->d_dedupe, &ctx->d_keys, &ctx->d_trimctl})
+                      &ctx->d_small, &ctx->d_states, &ctx->d_dedupe, &ctx->d_keys, &ctx->d_trimctl, &ctx->d_hex})
         if (b->p) cudaFree(b->p);
     for (auto& r : ctx->stream_pool) stream_res_destroy(r);
     ctx->stream_pool.clear();
@@ -979,7 +996,8 @@ int b200h_hash_batch_host(b200h_ctx* ctx, const uint8_t* base, const uint64_t* o
                           uint64_t* trimmed_len_out) {
     if (!ctx) return B200H_E_INVALID;
     B200H_RANGE("b200h_hash_batch_host");
-    if (n && n <= kCombineMaxN && ctx->combine_enabled && offsets && lengths && (flags & (B200H_SHA256 | B200H_MD5)))
+    if (n && n <= kCombineMaxN && ctx->combine_enabled && offsets && lengths && (flags & (B200H_SHA256 | B200H_MD5)) &&
+        !(flags & B200H_HEX_OUT))
         return combined_hash_batch_host(ctx, base, offsets, lengths, n, flags & kPublicFlags, sha256_out, md5_out,
                                         trimmed_len_out);
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -998,9 +1016,25 @@ int b200h_hash_batch_device_hl(b200h_ctx* ctx, const void* d_base, const uint64_
         return fail(ctx, B200H_E_INVALID, "digest outputs must be 16-byte aligned");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->s_comp;
-    return enqueue_device_batch(ctx, (const uint8_t*)d_base, d_offsets, d_lengths, n, flags & kPublicFlags,
-                                (flags & B200H_SHA256) ? (uint8_t*)d_sha256 : nullptr,
-                                (flags & B200H_MD5) ? (uint8_t*)d_md5 : nullptr, d_trimmed_len, nullptr, st, h_lengths);
+    uint8_t* o_sha = (flags & B200H_SHA256) ? (uint8_t*)d_sha256 : nullptr;
+    uint8_t* o_md5 = (flags & B200H_MD5) ? (uint8_t*)d_md5 : nullptr;
+    if (!(flags & B200H_HEX_OUT) || !n)
+        return enqueue_device_batch(ctx, (const uint8_t*)d_base, d_offsets, d_lengths, n, flags & kPublicFlags, o_sha, o_md5,
+                                    d_trimmed_len, nullptr, st, h_lengths);
+    // hex columns: the kernels write raw rows into library scratch, hex_rows_kernel expands them into the caller's
+    // (twice as wide) buffers, all on `st`
+    if (ctx->scratch_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
+    if (int rc = ensure_dev(ctx, ctx->d_hex, n * 48 + 64)) return rc;
+    uint8_t* raw_sha = (uint8_t*)ctx->d_hex.p;
+    uint8_t* raw_md5 = raw_sha + n * 32;
+    if (int rc = enqueue_device_batch(ctx, (const uint8_t*)d_base, d_offsets, d_lengths, n, flags & kPublicFlags,
+                                      o_sha ? raw_sha : nullptr, o_md5 ? raw_md5 : nullptr, d_trimmed_len, nullptr, st, h_lengths))
+        return rc;
+    if (o_sha) ctx->launches += launch_hex_rows(raw_sha, n * 32, o_sha, st);
+    if (o_md5) ctx->launches += launch_hex_rows(raw_md5, n * 16, o_md5, st);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_scratch, st));  // d_hex is shared scratch like the planner's
+    return 0;
 }
 
 int b200h_hash_batch_device(b200h_ctx* ctx, const void* d_base, const uint64_t* d_offsets, const uint64_t* d_lengths,

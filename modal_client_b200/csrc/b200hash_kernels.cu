@@ -135,6 +135,9 @@ __device__ __forceinline__ uint32_t addv(uint32_t a, uint32_t b) {
 #ifndef B200H_SHAONLY_ROT
 #define B200H_SHAONLY_ROT 3
 #endif
+#ifndef B200H_FUSED_ROT
+#define B200H_FUSED_ROT 0
+#endif
 __device__ __forceinline__ void rotw(uint32_t x, uint32_t mul, uint32_t& lo, uint32_t& hi) {
     uint64_t d;
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(x), "r"(mul));
@@ -262,7 +265,9 @@ __device__ __forceinline__ void compress(uint32_t (&hs)[8], uint32_t (&hm)[4], c
     constexpr bool kPlainAdd = SPARSE;
     uint32_t w[16];
     uint32_t m14 = x[14], m15 = x[15];
-    constexpr int kShaRot = (DO_MD5 || SPARSE) ? 0 : (B200H_SHAONLY_ROT);  // multiplies add instructions: dense only
+    // multiplies add instructions: dense instantiations only.  B200H_FUSED_ROT (default 0) is the same knob for the fused
+    // kernel; measured in round 2 (profiles/r2_kernel_lever.md): bit 2 (sigma shifts as IMAD.HI) does not pay there either.
+    constexpr int kShaRot = SPARSE ? 0 : (DO_MD5 ? (B200H_FUSED_ROT) : (B200H_SHAONLY_ROT));
     const uint32_t m29 = one << 29, m22 = one << 22;  // 2^29, 2^22 as run-time values (bit 2 of kShaRot)
     (void)m29; (void)m22;
     if (DO_SHA) {
@@ -1514,6 +1519,38 @@ __global__ void fill_synth_kernel(uint8_t* __restrict__ dst, uint64_t nbytes, ui
             for (uint64_t b = 0; b < (nbytes & 7); ++b) dst[8 * nwords + b] = (uint8_t)(v >> (8 * b));
         }
     }
+}
+
+// Lowercase hex of a byte table (the wire form of MountFile.sha256_hex / md5_hex, modal_proto/api.proto:2582-2587):
+// one thread turns 4 digest bytes into 8 ASCII characters, so a whole digest column leaves the device already in
+// the form the RPC rows carry.  nbytes is a multiple of 16 (whole rows).
+__global__ void hex_rows_kernel(const uint32_t* __restrict__ in, uint64_t nwords, uint2* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = in[i];  // bytes b0..b3 little-endian
+        uint32_t o[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t b = (w >> (16 * h + 8 * k)) & 0xffu;
+                const uint32_t hi = b >> 4, lo = b & 15u;
+                const uint32_t ch = (hi < 10 ? hi + 48u : hi + 87u), cl = (lo < 10 ? lo + 48u : lo + 87u);
+                acc |= (ch | (cl << 8)) << (16 * k);
+            }
+            o[h] = acc;
+        }
+        out[i] = make_uint2(o[0], o[1]);
+    }
+}
+
+int launch_hex_rows(const uint8_t* in, uint64_t nbytes, uint8_t* out, cudaStream_t st) {
+    if (!nbytes) return 0;
+    const uint64_t nwords = nbytes / 4;
+    uint64_t g = (nwords + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    hex_rows_kernel<<<(int)g, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(in), nwords, reinterpret_cast<uint2*>(out));
+    return 1;
 }
 
 // --------------------------------------------------------------------------------- launch wrappers

@@ -57,6 +57,8 @@ uint32_t dedupe_table_capacity(uint64_t n);  // slots; the table buffer holds 2x
 int launch_dedupe(const void* d_keys, uint64_t n, uint32_t key_bytes, uint32_t* table, uint32_t* d_first,
                   unsigned long long* d_ndistinct, cudaStream_t st);
 int launch_fill_synth(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t start, cudaStream_t st);
+// out[2*nbytes] = lowercase ASCII hex of in[nbytes] (nbytes a multiple of 4, both 8-byte aligned)
+int launch_hex_rows(const uint8_t* in, uint64_t nbytes, uint8_t* out, cudaStream_t st);
 
 int chain_groups_per_cta();        // long messages one chain CTA can host (one CTA per SM)
 cudaError_t configure_kernels();  // one-time cudaFuncSetAttribute calls for the current device

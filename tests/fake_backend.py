@@ -9,6 +9,15 @@ from modal_client_b200 import _lib
 from oracle import c_oracle
 
 
+def _hexed(table, flags):
+    """What B200H_HEX_OUT does on the device: rows as lowercase ASCII hex."""
+    if table is None or not (flags & _lib.HEX_OUT):
+        return table
+    t = np.ascontiguousarray(table, np.uint8)
+    return np.frombuffer(t.tobytes().hex().encode("ascii"), np.uint8).reshape(t.shape[0], 2 * t.shape[1]) if t.size else \
+        np.zeros((t.shape[0], 2 * t.shape[1]), np.uint8)
+
+
 def _u8(b) -> np.ndarray:
     return b if isinstance(b, np.ndarray) else np.frombuffer(b, dtype=np.uint8)
 
@@ -50,7 +59,7 @@ class FakeContext:
                 sha[i] = np.frombuffer(c_oracle.sha256(a), np.uint8)
             if md5 is not None:
                 md5[i] = np.frombuffer(c_oracle.md5(a), np.uint8)
-        return sha, md5, ln
+        return _hexed(sha, flags), _hexed(md5, flags), ln
 
     def hash_batch_host(self, base, offsets, lengths, flags=_lib.SHA256 | _lib.MD5):
         self.calls.append(("hash_batch_host", len(offsets), flags))
@@ -66,7 +75,7 @@ class FakeContext:
             base, off = total, pos
         s, m, e = c_oracle.hash_batch(_u8(base), off, ln, sha=bool(flags & _lib.SHA256), md5=bool(flags & _lib.MD5),
                                       trim=bool(flags & _lib.TRIM_ZEROS))
-        return s, m, e
+        return _hexed(s, flags), _hexed(m, flags), e
 
     def hash_fixed_parts(self, data, part_len, flags=_lib.SHA256 | _lib.MD5, want_etag=False):
         self.calls.append(("hash_fixed_parts", part_len, flags))
@@ -120,5 +129,6 @@ class FakeContext:
                 md5s.append(m)
             lens.append(e)
         cat = lambda xs, w: (np.concatenate(xs) if xs else np.zeros((0, w), np.uint8))  # noqa: E731
-        return (cat(shas, 32) if flags & _lib.SHA256 else None, cat(md5s, 16) if flags & _lib.MD5 else None,
+        return (_hexed(cat(shas, 32), flags) if flags & _lib.SHA256 else None,
+                _hexed(cat(md5s, 16), flags) if flags & _lib.MD5 else None,
                 np.concatenate(lens) if lens else np.zeros(0, np.uint64))

@@ -277,3 +277,42 @@ def test_single_message_of_4gib_plus_1(plain_ctx):
     assert int(trimmed[0]) == n
     assert sha[0].tobytes() == hashlib.sha256(data).digest()
     assert md5[0].tobytes() == hashlib.md5(data).digest()
+
+
+# ------------------------------------------------------------------------------------- hex columns (B200H_HEX_OUT)
+
+
+def test_hex_columns_formatted_on_the_device(plain_ctx, tmp_path):
+    """The digest columns as lowercase ASCII hex (the text MountFile.sha256_hex / FileUploadSpec.md5_hex carry), from
+    the host entry point, the file reader and the device entry point."""
+    import torch
+
+    ctx = plain_ctx
+    offs, lens = _layout([0, 1, 55, 64, 4096, 300_001, 65536, 200_000])
+    buf = synth_array(41, int(offs[-1] + lens[-1]) + 8)
+    want_sha = [hashlib.sha256(buf[int(o) : int(o + n)]).hexdigest() for o, n in zip(offs, lens)]
+    want_md5 = [hashlib.md5(buf[int(o) : int(o + n)]).hexdigest() for o, n in zip(offs, lens)]
+    sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, BOTH | _lib.HEX_OUT)
+    assert sha.shape == (len(lens), 64) and md5.shape == (len(lens), 32)
+    assert [r.tobytes().decode() for r in sha] == want_sha and [r.tobytes().decode() for r in md5] == want_md5
+    sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, _lib.SHA256 | _lib.HEX_OUT)
+    assert md5 is None and [r.tobytes().decode() for r in sha] == want_sha
+    paths = []
+    for i, (o, n) in enumerate(zip(offs, lens)):
+        p = tmp_path / f"f{i}"
+        buf[int(o) : int(o + n)].tofile(p)
+        paths.append(str(p))
+    sizes, _ = ctx.stat_files(paths)
+    sha, md5, _ = ctx.hash_files(paths, sizes, 0, BOTH | _lib.HEX_OUT)
+    assert [r.tobytes().decode() for r in sha] == want_sha and [r.tobytes().decode() for r in md5] == want_md5
+    dev = torch.device("cuda:0")
+    d = torch.from_numpy(buf).to(dev)
+    d_off = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    d_len = torch.from_numpy(lens.astype(np.int64)).to(dev)
+    h_sha = torch.zeros((len(lens), 64), dtype=torch.uint8, device=dev)
+    h_md5 = torch.zeros((len(lens), 32), dtype=torch.uint8, device=dev)
+    ctx.hash_batch_device(d.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), len(lens), BOTH | _lib.HEX_OUT, h_sha.data_ptr(),
+                          h_md5.data_ptr(), 0, torch.cuda.current_stream().cuda_stream, h_lengths=lens)
+    torch.cuda.synchronize()
+    assert [bytes(r).decode() for r in h_sha.cpu().numpy()] == want_sha
+    assert [bytes(r).decode() for r in h_md5.cpu().numpy()] == want_md5

@@ -386,3 +386,40 @@ def test_patchable_constants_equal_the_references():
         "network_file_system.py", "NETWORK_FILE_SYSTEM_PUT_FILE_CLIENT_TIMEOUT")
     assert parallel_map.MAP_INVOCATION_CHUNK_SIZE == ref_const("parallel_map.py", "MAP_INVOCATION_CHUNK_SIZE")
     assert parallel_map.SPAWN_MAP_INVOCATION_CHUNK_SIZE == ref_const("parallel_map.py", "SPAWN_MAP_INVOCATION_CHUNK_SIZE")
+
+
+def test_batched_specs_hash_the_bytes_they_cache_and_redo_files_that_grew(fake_backend, tmp_path, monkeypatch):
+    """(1) a cached-content file is read once and exactly those bytes are hashed; (2) a file that grew between
+    the stat and the read is not silently reported with the digest of its old prefix."""
+    import hashlib
+
+    small = tmp_path / "small.bin"
+    small.write_bytes(b"s" * 1000)
+    grown = tmp_path / "grown.bin"
+    grown.write_bytes(b"g" * 300_000)  # streamed class (>= 256 KiB)
+    real_stat = fake_backend.stat_files
+    calls = {"n": 0}
+
+    def stale_first_stat(paths):
+        sizes, modes = real_stat(paths)
+        calls["n"] += 1
+        if calls["n"] == 1:  # what a stat taken before the file was appended to would have said
+            sizes = sizes.copy()
+            sizes[[i for i, p in enumerate(paths) if p.endswith(b"grown.bin")]] = 299_000
+        return sizes, modes
+
+    monkeypatch.setattr(fake_backend, "stat_files", stale_first_stat)
+    reads = []
+    real_open = open
+
+    def counting_open(path, *a, **k):
+        reads.append(str(path))
+        return real_open(path, *a, **k)
+
+    monkeypatch.setattr("builtins.open", counting_open)
+    specs = blob_utils.get_file_upload_specs([(small, "small.bin", None), (grown, "grown.bin", None)], cache_small_content=True)
+    monkeypatch.undo()
+    assert specs[0].content == b"s" * 1000 and specs[0].sha256_hex == hashlib.sha256(b"s" * 1000).hexdigest()
+    assert sum(1 for r in reads if r.endswith("small.bin")) == 1, "the cached file must be read exactly once"
+    assert specs[1].size == 300_000 and specs[1].sha256_hex == hashlib.sha256(b"g" * 300_000).hexdigest()
+    assert specs[1].md5_hex == hashlib.md5(b"g" * 300_000).hexdigest()
