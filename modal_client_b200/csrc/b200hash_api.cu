@@ -115,6 +115,8 @@ struct b200h_ctx {
     bool chain_enabled = true;
     // One chain CTA per SM, each hosting up to chain_groups_per_cta() messages (set from the SM count at create).
     uint32_t chain_cap = 592;
+    uint32_t sm_count = 148;
+    bool yield_chain_sms = true;  // B200H_YIELD_CHAIN_SMS=0: lane CTAs share SMs with chain CTAs (round-1 behaviour)
     int* h_plan = nullptr;        // pinned: the planner's control block {avail, head, tail, outliers} of the last batch
     uint32_t last_outliers = 0;
     bool verify_plan = false;     // B200H_VERIFY_PLAN=1: cross-check the host-side outlier count against the device's
@@ -402,7 +404,10 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     }
     cudaEvent_t pa, pb;
     if (int rc = prof_begin(ctx, st, &pa, &pb)) return rc;
-    ctx->launches += launch_lane_hash(d_base, d_off, len_used, ring, qctl, n, kflags, d_sha, d_md5, states, st);
+    // Lane CTAs leave the SMs that host a live chain CTA to the chains (they set the makespan) -- as long as enough SMs
+    // stay chain-free for the lane work (chain CTAs sit on at most n_chain SMs, one each).
+    const uint32_t lane_flags = (n_chain && n_chain <= ctx->sm_count * 3 / 4 && ctx->yield_chain_sms) ? (kflags | F_YIELD_CHAIN_SMS) : kflags;
+    ctx->launches += launch_lane_hash(d_base, d_off, len_used, ring, qctl, n, lane_flags, d_sha, d_md5, states, st);
     if (int rc = prof_end(ctx, st, pa, pb)) return rc;
     if (n_chain && shared_scratch) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU_TRY(ctx, cudaGetLastError());
@@ -886,6 +891,8 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
     }
     CU_INIT(configure_kernels());
     ctx->chain_cap = (uint32_t)std::min<long>((long)prop.multiProcessorCount * chain_groups_per_cta(), (long)kMaxChain);
+    ctx->sm_count = (uint32_t)prop.multiProcessorCount;
+    if (const char* e = getenv("B200H_YIELD_CHAIN_SMS")) ctx->yield_chain_sms = atoi(e) != 0;
     CU_INIT(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
     CU_INIT(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
     {
@@ -914,18 +921,31 @@ int b200h_create(int device, size_t pinned_bytes, size_t device_bytes, b200h_ctx
     ctx->dwave_want = std::max<size_t>((device_bytes / 2) & ~size_t(255), 1 << 20);
     for (int s = 0; s < 2; ++s) CU_INIT(cudaHostAlloc(&ctx->pin[s], ctx->pin_cap, cudaHostAllocDefault));
     unsigned hc = std::thread::hardware_concurrency();
-    // One process per GPU shares the host with its siblings: with LOCAL_WORLD_SIZE ranks (torchrun) each keeping two
-    // batches in flight, 16 packers per context oversubscribe the cores (8 ranks x 2 x 16 = 256 threads on 128 CPUs)
-    unsigned share = hc;
-    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
-        const int lw = atoi(e);
-        if (lw > 1) share = std::max(4u, hc / (unsigned)lw);
-    }
-    ctx->pack_threads = (int)std::min(16u, std::max(1u, share / 2));  // measured best on 2x Xeon 8562Y+ (8..64 tried)
     {
         const char* e = getenv("B200H_NUMA");
         if (!(e && atoi(e) == 0)) ctx->node_cpus_valid = gpu_node_cpus(device, &ctx->node_cpus);
     }
+    // One process per GPU shares the host with its siblings.  The packers run on the GPU's NUMA node, so what a rank
+    // may use is that node's CPUs divided by the ranks whose GPUs hang off the same node (LOCAL_WORLD_SIZE ranks spread
+    // over the nodes), and a caller that keeps two batches in flight (the map pump) runs two packer teams at once:
+    // 8 ranks x 2 x 16 packers were 256 threads on 128 CPUs in the first 8-GPU run of the pump (profiles/r2_scaling.md).
+    unsigned share = ctx->node_cpus_valid ? (unsigned)CPU_COUNT(&ctx->node_cpus) : hc;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+        const int lw = atoi(e);
+        if (lw > 1) {
+            unsigned nodes = 0;
+            if (ctx->node_cpus_valid) {
+                for (int k = 0; k < 64; ++k) {
+                    char path[64];
+                    snprintf(path, sizeof path, "/sys/devices/system/node/node%d", k);
+                    if (access(path, F_OK) == 0) ++nodes;
+                }
+            }
+            const unsigned per_node = nodes ? ((unsigned)lw + nodes - 1) / nodes : (unsigned)lw;
+            share = std::max(4u, share / std::max(1u, per_node));
+        }
+    }
+    ctx->pack_threads = (int)std::min(16u, std::max(2u, share / 2));  // 16: measured best on 2x Xeon 8562Y+ (8..64 tried)
     if (const char* e = getenv("B200H_PACK_THREADS")) ctx->pack_threads = std::max(1, atoi(e));
     ctx->io_threads = (int)std::min(16u, std::max(1u, share));  // measured: 16 > 32 > 64 > 128 (kernel-side contention)
     if (const char* e = getenv("B200H_IO_THREADS")) ctx->io_threads = std::max(1, atoi(e));

@@ -471,6 +471,16 @@ lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
     constexpr bool kPairGather = (B200H_PAIR_GATHER != 0) && !(DO_SHA && DO_MD5) && !kOctetGather;
     const bool final = !(flags & F_NO_FINAL);
     const bool lane_on = lane < lanes_per_warp;
+    if (flags & F_YIELD_CHAIN_SMS) {
+        // This SM hosts a chain CTA that carries one of the batch's longest messages: the chain's round warp issues at
+        // most one instruction every two cycles and every lane warp next to it on the SMSP takes slots away from the
+        // one chain that sets the makespan (C3-v2, 93 chains + 12.5 GiB of lane work per GPU: 327 ms with shared SMs).
+        // The queue makes leaving free: whatever this CTA would have hashed is pulled by the CTAs on the other SMs.
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const uint32_t* sm_flags = reinterpret_cast<const uint32_t*>(qctl) + kSmFlagsAfterQctl;
+        if (smid < (uint32_t)kSmFlagWords && ld_volatile_u32(sm_flags + smid) != 0u) return;
+    }
 
     // ---- per-lane message context
     bool has = false;
@@ -931,6 +941,12 @@ chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
     constexpr bool kPlainAdd = false;  // ADD() inside CH_RND: the one off-path sum stays an IMAD
     const uint32_t n_chain = (uint32_t)qctl[3];
     if (blockIdx.x >= n_chain) return;  // entry e lives in CTA e % gridDim.x: this CTA has none
+    if (threadIdx.x == 0) {  // tell lane CTAs that this SM is taken (F_YIELD_CHAIN_SMS)
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (smid < (uint32_t)kSmFlagWords)
+            st_volatile_u32(const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(qctl)) + kSmFlagsAfterQctl + smid, 1u);
+    }
     extern __shared__ __align__(128) uint8_t smem_all[];
     const int lane = threadIdx.x & 31;
     const int grp = (threadIdx.x >> 5) / 3;   // which of the CTA's messages
@@ -1592,6 +1608,7 @@ int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* chain
     int* qctl = plan_qctl(scratch);
     unsigned long long* total = reinterpret_cast<unsigned long long*>(scratch + 2 * kPlanBuckets + 4);
     cudaMemsetAsync(hist, 0, sizeof(uint32_t) * kPlanBuckets, st);
+    cudaMemsetAsync(reinterpret_cast<uint32_t*>(qctl) + kSmFlagsAfterQctl, 0, sizeof(uint32_t) * kSmFlagWords, st);
     cudaMemsetAsync(total, 0, sizeof(unsigned long long), st);
     cudaMemsetAsync(ring, 0xff, sizeof(uint32_t) * ring_capacity(n), st);
     plan_hist_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, hist, total);

@@ -18,13 +18,16 @@ enum : uint32_t {
     F_MD5 = 2u,
     F_TRIM = 4u,      // hash the zero-trimmed prefix of every message, report trimmed length
     F_NO_FINAL = 8u,  // continuation segment: len % 64 == 0, no padding, write ChainState back
+    F_YIELD_CHAIN_SMS = 16u,  // lane kernel: a CTA that lands on an SM hosting a live chain CTA exits at once
 };
 
 constexpr int kPlanBuckets = 512;
 constexpr unsigned long long kChainMinBlocks = 1024;  // 64 KiB: shorter messages never go to the chain kernel
 constexpr unsigned long long kChainRatio = 24000;     // lane kernel ~700 GB/s vs ~29 MB/s for one lane
 constexpr uint32_t kMaxChain = 1184;                  // chain-list capacity (entries)
-constexpr int kPlanScratchWords = 2 * kPlanBuckets + 8;  // hist, cursor, qctl[4], total_blocks (u64), pad
+constexpr int kSmFlagWords = 256;  // one word per SM: set by a chain CTA that serves a message (see F_YIELD_CHAIN_SMS)
+// hist, cursor, qctl[4], total_blocks (u64), pad[2], sm_flags[kSmFlagWords]
+constexpr int kPlanScratchWords = 2 * kPlanBuckets + 8 + kSmFlagWords;
 
 // Launch wrappers (defined in b200hash_kernels.cu).  All asynchronous on `st`.
 // Every wrapper returns the number of kernels it launched (for gpu_launches accounting).
@@ -44,6 +47,8 @@ uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain)
 uint32_t ring_capacity(uint64_t n);  // power of two >= max(n, 32): entries of the work-queue ring
 // scratch layout (uint32 words): hist[kPlanBuckets] | cursor[kPlanBuckets] | qctl[4] | total_blocks (u64) | pad
 inline int* plan_qctl(uint32_t* scratch) { return reinterpret_cast<int*>(scratch + 2 * kPlanBuckets); }
+// the per-SM flags live 8 words behind qctl (device code reaches them through the qctl pointer it already has)
+constexpr int kSmFlagsAfterQctl = 8;
 int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring /*ring_capacity(n)*/, uint32_t* chain_list /*kMaxChain*/,
                 uint32_t* scratch /*kPlanScratchWords*/, bool fresh, uint32_t max_chain, cudaStream_t st);
 int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* chain_list,

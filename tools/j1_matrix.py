@@ -109,11 +109,15 @@ def gpu_row(name, data, offs, lens, flags, reps=2, gather=True, warm=True, e2e=T
     recv = torch.empty(world * cap * 56, dtype=torch.uint8, device=dev) if world > 1 and gather else None
     trim = bool(flags & _lib.TRIM_ZEROS)
 
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
     def step():
         # lengths are known on the host -> the call only enqueues (trim mode: the planner's count is read back)
+        h0.record(st)
         ctx.hash_batch_device(data.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), n, flags,
                               sha_p if flags & _lib.SHA256 else 0, md5_p if flags & _lib.MD5 else 0, tr_p, st.cuda_stream,
                               h_lengths=None if trim else lens)
+        h1.record(st)  # this rank's own makespan ends here; the all-gather then waits for the slowest rank
         if recv is not None:
             dist.all_gather_into_tensor(recv, rows)
 
@@ -129,6 +133,7 @@ def gpu_row(name, data, offs, lens, flags, reps=2, gather=True, warm=True, e2e=T
     my_ms = e0.elapsed_time(e1) / reps
     ms = allmax(my_ms)
     per_rank_ms = allgather_floats(my_ms)
+    per_rank_hash_ms = allgather_floats(h0.elapsed_time(h1))  # last pass, hash only (before the gather)
     my_bytes = float(lens.astype(np.float64).sum())
     total = allsum(my_bytes)
     outliers = ctx.last_outlier_count
@@ -161,7 +166,7 @@ def gpu_row(name, data, offs, lens, flags, reps=2, gather=True, warm=True, e2e=T
     gbps = total / 1e9 / (ms / 1e3)
     emit({"config": name, "n_gpus": world, "messages_total": int(allsum(n)), "bytes_total": int(total),
           "kernel_ms": round(ms, 3), "kernel_GiBps": round(total / GiB / (ms / 1e3), 2), "kernel_GBps": round(gbps, 1),
-          "hbm_frac_per_gpu": round(gbps / world / PEAK, 4), "per_rank_ms": per_rank_ms,
+          "hbm_frac_per_gpu": round(gbps / world / PEAK, 4), "per_rank_ms": per_rank_ms, "per_rank_hash_ms": per_rank_hash_ms,
           "e2e_GiBps": round(e2e_gibs, 2) if e2e_gibs else None,
           "e2e_bytes": int(e2e_bytes_total) if e2e_bytes_total else None, "e2e_equals_kernel_digests": same,
           "outliers_on_rank0": outliers, "flags": flags, **extra})
