@@ -70,3 +70,60 @@ def test_c_host_blob_upload_matches_hashlib(exe):
     assert "put_error failed blob upload: 500" in text
     launches = int(re.search(r"many_launches (\d+)", text).group(1))
     assert launches <= 6  # 300 payloads: ONE batch (3 plan kernels + chain + lane_hash launches), not 300 hash calls
+
+
+# ---------------------------------------------------------------------------- JS SDK: the N-API addon (js/src/blob.ts)
+
+
+@pytest.fixture(scope="module")
+def napi_exe(tmp_path_factory):
+    """bindings/node/b200hash_napi.c compiled as strict C99 against tests/c/node_api.h (stand-in for the Node-API subset
+    it uses; Node itself is not in this image) together with the C driver that plays Node's part."""
+    _lib.build_library()
+    out = str(tmp_path_factory.mktemp("napi") / "napi_host_check")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    inc = ["-I", os.path.join(ROOT, "tests", "c"), "-I", os.path.join(ROOT, "include")]
+    addon = os.path.join(ROOT, "bindings", "node", "b200hash_napi.c")
+    strict = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", *inc, addon],
+                            capture_output=True, text=True)
+    assert strict.returncode == 0, strict.stderr
+    cmd = ["gcc", "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-O1", "-Wall", "-Wextra", "-Werror", *inc,
+           os.path.join(ROOT, "tests", "c", "napi_host_check.c"), addon, "-o", out, "-L", libdir, "-l:libb200hash.so",
+           f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+def _js_payload(i: int, n: int) -> bytes:
+    k = np.arange(n, dtype=np.uint64)
+    return ((np.uint64(i * 131) + k * np.uint64(7) + np.uint64(1)) & np.uint64(0xff)).astype(np.uint8).tobytes()
+
+
+def test_napi_addon_compiles_and_throws_without_gpu(napi_exe):
+    import json
+
+    r = subprocess.run([napi_exe, "10", "20"], capture_output=True, text=True, timeout=120)
+    out = json.loads(r.stdout)
+    if "error" in out:  # no B200 here: the JS side sees an exception, never a CPU digest
+        assert "no CPU fallback" in out["error"] and r.returncode == 1
+    else:
+        assert len(out["md5"]) == 2
+
+
+@pytest.mark.gpu
+def test_napi_addon_hashes_many_matches_node_crypto_semantics(napi_exe):
+    """exports.hashesMany(Uint8Array[]) == createHash(..).update(data).digest("base64") per payload
+    (js/src/blob.ts:35-36), in one GPU batch; exports.shouldUpload is the strict 2 MiB gate."""
+    import json
+
+    sizes = [0, 1, 55, 64, 1000, 65536, 300001, 2 * 1024 * 1024 + 1]
+    r = subprocess.run([napi_exe, *map(str, sizes)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout)
+    for i, n in enumerate(sizes):
+        data = _js_payload(i, n)
+        assert out["md5"][i] == base64.b64encode(hashlib.md5(data).digest()).decode()
+        assert out["sha256"][i] == base64.b64encode(hashlib.sha256(data).digest()).decode()
+    assert out["should_upload_2MiB"] is False and out["should_upload_2MiB_plus_1"] is True
+    assert out["throws_on_non_array"] is True
