@@ -24,6 +24,38 @@ def should_upload(num_bytes: int, max_object_size_bytes: int, function_call_invo
     )
 
 
+class DevicePayload:
+    """A serialized function input that already lives in HBM: ``tensor`` is a contiguous CUDA tensor whose raw bytes ARE
+    the wire payload (what a GPU-side serializer produced, or a tensor argument shipped raw).  A serializer hook may
+    return one instead of ``bytes``; the map pump then digests it where it is (``batch.hash_table_tensors``: no
+    host->device copy, nothing pickled through host memory) and copies it to the host once, for the PUT
+    (the reference pickles tensor arguments on the CPU, py/modal/_utils/function_utils.py:577-621)."""
+
+    __slots__ = ("tensor",)
+
+    def __init__(self, tensor):
+        if not (getattr(tensor, "is_cuda", False) and tensor.is_contiguous()):
+            raise ValueError("DevicePayload needs a contiguous CUDA tensor")
+        self.tensor = tensor
+
+    def __len__(self) -> int:
+        return self.tensor.numel() * self.tensor.element_size()
+
+    def to_bytes(self) -> bytes:
+        import torch
+
+        flat = self.tensor.reshape(-1).view(torch.uint8)
+        return flat.cpu().numpy().tobytes()
+
+
+def hash_device_payloads(payloads: Sequence["DevicePayload"], ctx=None):
+    """(sha256 uint8[n,32], md5 uint8[n,16]) numpy tables of payloads resident in HBM, hashed in place in one batch."""
+    from . import batch
+
+    d_sha, d_md5 = batch.hash_table_tensors([p.tensor for p in payloads], ctx=ctx)
+    return d_sha.cpu().numpy(), d_md5.cpu().numpy()
+
+
 def serialize_pickle(obj: Any) -> bytes:
     """cloudpickle protocol 4, like the reference's ``serialize`` (py/modal/_serialization.py:102-106)."""
     import cloudpickle

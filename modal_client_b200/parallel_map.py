@@ -28,7 +28,8 @@ from typing import Any
 from . import _backend, _wire, blob_utils, hash_utils
 from ._logging import logger
 from .async_utils import bounded_map_ordered
-from .function_utils import _blob_item, _function_fields, _inline_item, serialize_data_format
+from . import function_utils
+from .function_utils import DevicePayload, _blob_item, _function_fields, _inline_item, serialize_data_format
 
 MAP_INVOCATION_CHUNK_SIZE = 49  # inputs per FunctionPutInputs request (sync map)
 SPAWN_MAP_INVOCATION_CHUNK_SIZE = 512
@@ -47,13 +48,14 @@ _END = object()
 class _Window:
     """One hash window: the serialized payloads of consecutive inputs and which of them go to blob storage."""
 
-    __slots__ = ("first_idx", "payloads", "big", "hashes")
+    __slots__ = ("first_idx", "payloads", "big", "hashes", "big_payloads")
 
     def __init__(self, first_idx: int):
         self.first_idx = first_idx
         self.payloads: list[bytes] = []
         self.big: list[int] = []  # positions (within the window) of payloads above the threshold
         self.hashes = None  # future -> sequence of UploadHashes, one per entry of `big`
+        self.big_payloads: list | None = None  # the payloads of `big` as handed to the hash call
 
 
 class _WindowedInputPipeline:
@@ -121,7 +123,9 @@ class _WindowedInputPipeline:
             def hash_window(c, payloads):
                 t = time.perf_counter()
                 try:
-                    return hash_utils.get_upload_hashes_many(payloads, ctx=c)
+                    if all(type(p) is bytes for p in payloads):
+                        return hash_utils.get_upload_hashes_many(payloads, ctx=c)
+                    return self._hash_mixed_window(c, payloads)
                 finally:
                     self.stats["hash_call_s"] += time.perf_counter() - t
 
@@ -136,6 +140,7 @@ class _WindowedInputPipeline:
                     ctx = await free.get()  # at most one batch per context at a time
                     self.stats["wait_context_s"] += time.perf_counter() - t0
                     big_payloads = [win.payloads[i] for i in win.big]
+                    win.big_payloads = big_payloads  # DevicePayloads are replaced by their host bytes in here
                     fut = loop.run_in_executor(None, hash_window, ctx, big_payloads)
                     fut.add_done_callback(lambda _f, c=ctx: free.put_nowait(c))
                     win.hashes = fut
@@ -143,6 +148,26 @@ class _WindowedInputPipeline:
                 await out.put(win)
         finally:
             await out.put(_END)
+
+    @staticmethod
+    def _hash_mixed_window(ctx, payloads):
+        """A window in which some payloads are ``DevicePayload``s: those are digested in HBM where they are (one
+        batch), the host ones as usual (one batch); the device ones are copied to the host once, for their PUT.
+        Returns a digest view in window order; ``payloads`` is updated in place with the materialised bytes."""
+        import numpy as np
+
+        dev = [i for i, p in enumerate(payloads) if type(p) is not bytes]
+        host = [i for i, p in enumerate(payloads) if type(p) is bytes]
+        n = len(payloads)
+        sha, md5 = np.empty((n, 32), np.uint8), np.empty((n, 16), np.uint8)
+        if host:
+            s, m, _ = ctx.hash_buffers([payloads[i] for i in host], hash_utils.SHA256 | hash_utils.MD5)
+            sha[host], md5[host] = s, m
+        s, m = function_utils.hash_device_payloads([payloads[i] for i in dev], ctx=ctx)
+        sha[dev], md5[dev] = s, m
+        for i in dev:
+            payloads[i] = payloads[i].to_bytes()  # the one device->host copy of this payload (its upload body)
+        return hash_utils._UploadHashesView(sha, md5, n)
 
     # ---- stage 3: upload, emit in order ---------------------------------------------------------------------
     async def run(self, emit: Callable[[Any], Any]) -> None:
@@ -173,7 +198,11 @@ class _WindowedInputPipeline:
                     win.payloads[pos] = None  # the window must not pin every payload until its last upload is done
                     k = big_pos.get(pos)
                     if k is None:
+                        if type(payload) is not bytes:  # a small DevicePayload stays inline: one copy to the host
+                            payload = payload.to_bytes()
                         return _inline_item(win.first_idx + pos, payload, self.data_format, self.method_name)
+                    if type(payload) is not bytes:
+                        payload, win.big_payloads[k] = win.big_payloads[k], None  # materialised by the hash stage
                     upload = await blob_utils._blob_upload_bytes(hashes[k], payload, self.stub)
                     return _blob_item(win.first_idx + pos, upload, self.data_format, self.method_name)
 

@@ -320,3 +320,97 @@ def test_bench_map_pump_leg_on_the_stand_in(fake_backend, monkeypatch):
         assert r.content_sha256_base64 == base64.b64encode(hashlib.sha256(p).digest()).decode()
         assert r.content_md5 == base64.b64encode(hashlib.md5(p).digest()).decode()
     assert sum(len(t[0]) for t in tables) == 50
+
+
+def _run_pump_with_device_payloads(make_device_payload, raw_bytes):
+    """Inputs alternate between ordinary bytes and payloads that live 'in HBM'; every one is above the blob threshold
+    except the last.  Returns (items, blob store, BlobCreate requests)."""
+    fn = types.SimpleNamespace(_use_method_name="", _max_object_size_bytes=5_000, _metadata=object(), object_id="fu-1")
+    out = {}
+
+    async def run():
+        async with running_blob_server() as (host, store):
+            stub = FakeBlobStub(host)
+            raw, done = asyncio.Queue(), asyncio.Queue()
+            for i, b in enumerate(raw_bytes):
+                raw.put_nowait(make_device_payload(b) if i % 2 == 0 else b)
+            raw.put_nowait(None)
+            pre = parallel_map.InputPreprocessor(types.SimpleNamespace(stub=stub), raw_input_queue=raw,
+                                                 processed_input_queue=done, function=fn, serializer=lambda p: p)
+            async for _ in pre.drain_input_generator():
+                pass
+            items = []
+            while (it := await done.get()) is not None:
+                items.append(it)
+            out.update(items=items, blobs=dict(store.blobs), requests=list(stub.requests))
+            await blob_utils.ClientSessionRegistry.close_session()
+
+    asyncio.run(run())
+    return out["items"], out["blobs"], out["requests"]
+
+
+def _check_device_payload_run(items, blobs, requests, raw_bytes):
+    import base64
+
+    assert [it.idx for it in items] == list(range(len(raw_bytes)))
+    by_len = {r.content_length: r for r in requests}
+    for it, b in zip(items, raw_bytes):
+        if len(b) > 5_000:
+            assert blobs[it.input.args_blob_id] == b  # the PUT body is the payload, wherever it lived
+            r = by_len[len(b)]
+            assert r.content_sha256_base64 == base64.b64encode(hashlib.sha256(b).digest()).decode()
+            assert r.content_md5 == base64.b64encode(hashlib.md5(b).digest()).decode()
+        else:
+            assert it.input.args == b and not it.input.args_blob_id
+
+
+def test_pump_takes_payloads_that_live_on_the_device(fake_backend, monkeypatch):
+    """SURVEY 8(f)4 wiring, host logic: a serializer may hand the pump a DevicePayload; it is digested by
+    function_utils.hash_device_payloads (in HBM on the real thing), copied to the host once for its PUT, and mixes
+    freely with ordinary bytes payloads in one window."""
+    from oracle import c_oracle
+
+    class HostStandIn:  # same surface as function_utils.DevicePayload, bytes kept on the host for the CPU test
+        def __init__(self, b):
+            self.b, self.copies = b, 0
+
+        def __len__(self):
+            return len(self.b)
+
+        def to_bytes(self):
+            self.copies += 1
+            return self.b
+
+    made = []
+
+    def make(b):
+        made.append(HostStandIn(b))
+        return made[-1]
+
+    def fake_hash_device_payloads(payloads, ctx=None):
+        import numpy as np
+
+        return (np.frombuffer(b"".join(c_oracle.sha256(p.b) for p in payloads), np.uint8).reshape(-1, 32),
+                np.frombuffer(b"".join(c_oracle.md5(p.b) for p in payloads), np.uint8).reshape(-1, 16))
+
+    monkeypatch.setattr(function_utils, "hash_device_payloads", fake_hash_device_payloads)
+    raw_bytes = [bytes([i + 1]) * (6_000 + 977 * i) for i in range(9)] + [b"tiny"]
+    items, blobs, requests = _run_pump_with_device_payloads(make, raw_bytes)
+    _check_device_payload_run(items, blobs, requests, raw_bytes)
+    assert all(p.copies == 1 for p in made)  # one device->host copy each, never more
+
+
+@pytest.mark.gpu
+def test_pump_hashes_cuda_tensor_payloads_in_hbm(gpu_backend):
+    """The same on the GPU: CUDA tensors as payloads, digested in place by batch.hash_table_tensors."""
+    import torch
+
+    raw_bytes = [bytes([i + 1]) * (6_000 + 977 * i) for i in range(9)] + [b"tiny"]
+    launches0 = gpu_backend.launch_count
+
+    def make(b):
+        return function_utils.DevicePayload(torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda())
+
+    items, blobs, requests = _run_pump_with_device_payloads(make, raw_bytes)
+    _check_device_payload_run(items, blobs, requests, raw_bytes)
+    assert gpu_backend.launch_count > launches0

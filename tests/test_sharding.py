@@ -68,3 +68,20 @@ def test_two_ranks_gloo_all_gather_full_table(tmp_path):
             assert t["sha"][i].tobytes() == hashlib.sha256(msg).digest()
             assert t["md5"][i].tobytes() == hashlib.md5(msg).digest()
     assert np.array_equal(tables[0]["sha"], tables[1]["sha"])
+
+
+@pytest.mark.gpu
+def test_sharded_table_over_nccl_matches_the_oracle():
+    """hash_table_sharded with the real backend: 2 ranks / 2 GPUs over NCCL when the box has them (one rank otherwise),
+    the gathered table compared with the C oracle on rank 0 (tools/sharded_check.py)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    n = 2 if torch.cuda.device_count() >= 2 else 1
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "sharded_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0 and "SHARDED CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
