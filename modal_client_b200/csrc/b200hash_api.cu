@@ -376,7 +376,7 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     uint32_t n_chain = 0;
     if (chain_on) {
         const bool mirrored = h_len != nullptr;
-        if (mirrored) n_chain = plan_outliers_host(h_len, n, max_chain);
+        if (mirrored) n_chain = plan_outliers_host(h_len, n, max_chain, ctx->sm_count);
         if (!mirrored || ctx->verify_plan) {
             CU_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, qctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU_TRY(ctx, cudaStreamSynchronize(st));

@@ -443,6 +443,11 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -476,10 +481,20 @@ lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
         // most one instruction every two cycles and every lane warp next to it on the SMSP takes slots away from the
         // one chain that sets the makespan (C3-v2, 93 chains + 12.5 GiB of lane work per GPU: 327 ms with shared SMs).
         // The queue makes leaving free: whatever this CTA would have hashed is pulled by the CTAs on the other SMs.
+        // The chain kernel is launched just before this one, on a high-priority stream, with at most one CTA per SM
+        // on at most 3/4 of the SMs: its CTAs are resident within microseconds.  Wait for them (bounded: if they are
+        // not all there after kYieldWaitNs we simply go ahead and share), then leave if this SM is taken.  Leaving
+        // happens here only, before a single message has been taken, so nothing can be stranded.
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        const uint32_t* sm_flags = reinterpret_cast<const uint32_t*>(qctl) + kSmFlagsAfterQctl;
-        if (smid < (uint32_t)kSmFlagWords && ld_volatile_u32(sm_flags + smid) != 0u) return;
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(qctl);
+        const uint32_t expected = ld_volatile_u32(q + kChainExpectedWord);
+        if (expected) {
+            const unsigned long long t0 = globaltimer_ns();
+            while (ld_volatile_u32(q + kChainStartedWord) < expected && globaltimer_ns() - t0 < kYieldWaitNs) {
+            }
+        }
+        if (smid < (uint32_t)kSmFlagWords && ld_volatile_u32(q + kSmFlagsAfterQctl + smid) != 0u) return;
     }
 
     // ---- per-lane message context
@@ -941,11 +956,13 @@ chain_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
     constexpr bool kPlainAdd = false;  // ADD() inside CH_RND: the one off-path sum stays an IMAD
     const uint32_t n_chain = (uint32_t)qctl[3];
     if (blockIdx.x >= n_chain) return;  // entry e lives in CTA e % gridDim.x: this CTA has none
-    if (threadIdx.x == 0) {  // tell lane CTAs that this SM is taken (F_YIELD_CHAIN_SMS)
+    if (threadIdx.x == 0) {  // tell lane CTAs that this SM is taken (F_YIELD_CHAIN_SMS), then that this CTA is resident
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if (smid < (uint32_t)kSmFlagWords)
-            st_volatile_u32(const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(qctl)) + kSmFlagsAfterQctl + smid, 1u);
+        uint32_t* q = const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(qctl));
+        if (smid < (uint32_t)kSmFlagWords) st_volatile_u32(q + kSmFlagsAfterQctl + smid, 1u);
+        __threadfence();
+        atomicAdd(q + kChainStartedWord, 1u);
     }
     extern __shared__ __align__(128) uint8_t smem_all[];
     const int lane = threadIdx.x & 31;
@@ -1389,11 +1406,30 @@ __host__ __device__ __forceinline__ uint64_t plan_bucket_min_blocks(uint32_t b) 
     return (uint64_t)(8 + mant) << (e - 3);
 }
 
+// Rule (3) of the chain selection, shared by the planner kernel and its host mirror.
+//   count          messages that satisfy rules (1) and (2)
+//   chain_blocks   lower bound of their 64-byte blocks (bucket lower bounds x bucket counts; buckets are 12.5 % wide)
+// Chain CTAs and lane CTAs that share an SM slow each other down badly (round 2, one rank's share of C3-v2: the blocks
+// of 1..4 MiB alone took 250 ms with 344 of them on chains spread over every SM, ~110 ms with all of them on lanes).  So:
+//   * up to 3/4 of the SMs' worth of outliers get an SM each, which the lane kernel then leaves alone (F_YIELD_CHAIN_SMS);
+//   * more than that only when (almost) nothing is left for the lanes -- a batch of equally long messages, where the
+//     chain kernel runs by itself at up to max_chain chains (4 per SM);
+//   * otherwise none.
+__host__ __device__ __forceinline__ uint32_t plan_chain_count(uint32_t count, unsigned long long chain_blocks,
+                                                             unsigned long long total_blocks, uint32_t n, uint32_t max_chain,
+                                                             uint32_t sm_count) {
+    if (count == 0 || count > max_chain) return 0u;  // all of them or none
+    if (count <= sm_count * 3 / 4) return count;
+    if (count == n) return count;
+    const unsigned long long rest = total_blocks > chain_blocks ? total_blocks - chain_blocks : 0ull;
+    return rest <= total_blocks / 4 ? count : 0u;
+}
+
 // Host mirror of plan_hist_kernel + plan_scan_kernel's chain selection: how many of these messages the planner will
 // hand to the chain kernel.  Same integer arithmetic on the same lengths, so the answer is the device's; callers
 // that hold the lengths on the host use it to size the chain launch WITHOUT reading qctl[3] back (no stream
 // synchronisation inside an enqueue).  B200H_VERIFY_PLAN=1 makes the API cross-check it against the device.
-uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain) {
+uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain, uint32_t sm_count) {
     if (!n || !max_chain) return 0;
     uint64_t longest = 0;
     unsigned long long total = 0;
@@ -1409,9 +1445,16 @@ uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain)
     if (thr < half) thr = half;
     // messages in buckets whose lower bound reaches thr (bucket lower bounds are monotone in the bucket index)
     uint64_t count = 0;
-    for (uint64_t i = 0; i < n; ++i)
-        if (plan_bucket_min_blocks(plan_bucket(len[i])) >= thr) ++count;
-    return count <= max_chain ? (uint32_t)count : 0u;
+    unsigned long long chain_blocks = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t lb = plan_bucket_min_blocks(plan_bucket(len[i]));
+        if (lb >= thr) {
+            ++count;
+            chain_blocks += lb;
+        }
+    }
+    if (count > max_chain) return 0u;
+    return plan_chain_count((uint32_t)count, chain_blocks, total, (uint32_t)n, max_chain, sm_count);
 }
 
 __global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ hist,
@@ -1451,13 +1494,16 @@ __global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, u
 //       159 -> 332 ms with 148 of them moved over).
 // qctl = {lane entries available, head, tail, chain count}.
 __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, int* __restrict__ qctl,
-                                 const unsigned long long* __restrict__ total_blocks, uint32_t n, uint32_t max_chain) {
+                                 const unsigned long long* __restrict__ total_blocks, uint32_t n, uint32_t max_chain,
+                                 uint32_t sm_count) {
     __shared__ uint32_t sh[kPlanBuckets];
     __shared__ uint32_t sh_chain, sh_top;
+    __shared__ unsigned long long sh_chain_blocks;
     const int t = threadIdx.x;
     if (t == 0) {
         sh_chain = 0;
         sh_top = 0;
+        sh_chain_blocks = 0;
     }
     const int rev = kPlanBuckets - 1 - t;  // position in longest-first order
     sh[t] = hist[rev];
@@ -1479,13 +1525,17 @@ __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __
     const bool mine = plan_bucket_min_blocks((uint32_t)rev) >= thr;
     const bool next = rev > 0 && plan_bucket_min_blocks((uint32_t)rev - 1) >= thr;
     if (mine && !next) atomicMax(&sh_chain, sh[t]);  // inclusive count of everything at least this long
+    if (mine && hist[rev]) atomicAdd(&sh_chain_blocks, (unsigned long long)hist[rev] * plan_bucket_min_blocks((uint32_t)rev));
     __syncthreads();
     if (t == 0) {
-        const uint32_t c = sh_chain <= max_chain ? sh_chain : 0u;  // rule (3): all of them or none
+        const uint32_t c = plan_chain_count(sh_chain, sh_chain_blocks, *total_blocks, n, max_chain, sm_count);
         qctl[0] = (int)(n - c);  // lane-queue entries available
         qctl[1] = 0;             // head ticket
         qctl[2] = (int)(n - c);  // tail ticket
         qctl[3] = (int)c;        // messages handed to the chain kernel
+        // qctl[4..5] hold total_blocks; [6] = chain CTAs the lane kernel may wait for, [7] = chain CTAs that started
+        qctl[kChainExpectedWord] = (int)(c <= sm_count * 3 / 4 ? c : 0u);
+        qctl[kChainStartedWord] = 0;
     }
 }
 
@@ -1602,6 +1652,7 @@ uint32_t ring_capacity(uint64_t n) {
 // caller-provided chaining states), ring[n-c..cap) = EMPTY; qctl = {n-c, 0, n-c, c}.
 int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* chain_list, uint32_t* scratch, bool fresh,
                 uint32_t max_chain, cudaStream_t st) {
+    const uint32_t sm_count = (uint32_t)g_sm_count;
     if (!n) return 0;
     uint32_t* hist = scratch;
     uint32_t* cursor = scratch + kPlanBuckets;
@@ -1612,7 +1663,7 @@ int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* chain
     cudaMemsetAsync(total, 0, sizeof(unsigned long long), st);
     cudaMemsetAsync(ring, 0xff, sizeof(uint32_t) * ring_capacity(n), st);
     plan_hist_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, hist, total);
-    plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor, qctl, total, (uint32_t)n, max_chain);
+    plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor, qctl, total, (uint32_t)n, max_chain, sm_count);
     plan_scatter_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, cursor, ring, chain_list, qctl,
                                                                 fresh ? kFresh : 0u);
     return 3;

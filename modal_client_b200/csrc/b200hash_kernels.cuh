@@ -43,12 +43,15 @@ struct TrimWideEntry {
 int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n, uint64_t* trimmed,
                 unsigned long long* wctl, TrimWideEntry* wlist, cudaStream_t st);
 // The planner's outlier count for these lengths, computed on the host (mirror of plan_scan_kernel's selection).
-uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain);
+uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain, uint32_t sm_count);
 uint32_t ring_capacity(uint64_t n);  // power of two >= max(n, 32): entries of the work-queue ring
 // scratch layout (uint32 words): hist[kPlanBuckets] | cursor[kPlanBuckets] | qctl[4] | total_blocks (u64) | pad
 inline int* plan_qctl(uint32_t* scratch) { return reinterpret_cast<int*>(scratch + 2 * kPlanBuckets); }
 // the per-SM flags live 8 words behind qctl (device code reaches them through the qctl pointer it already has)
 constexpr int kSmFlagsAfterQctl = 8;
+constexpr int kChainExpectedWord = 6;  // qctl[6]: chain CTAs the lane kernel's CTAs wait for before they look at the flags
+constexpr int kChainStartedWord = 7;   // qctl[7]: chain CTAs that have set their flag
+constexpr unsigned long long kYieldWaitNs = 200000;  // bound of that wait (0.2 ms; the chain CTAs are there in microseconds)
 int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring /*ring_capacity(n)*/, uint32_t* chain_list /*kMaxChain*/,
                 uint32_t* scratch /*kPlanScratchWords*/, bool fresh, uint32_t max_chain, cudaStream_t st);
 int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* chain_list,
