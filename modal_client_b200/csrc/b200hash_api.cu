@@ -143,7 +143,7 @@ struct b200h_ctx {
     uint8_t* dwave[2] = {nullptr, nullptr};
     size_t dwave_cap = 0;  // per slot
     size_t dwave_want = 0;
-    DevBuf d_off, d_len, d_order, d_trim, d_sha, d_md5, d_scratch, d_small, d_states, d_dedupe, d_keys, d_trimctl, d_hex;
+    DevBuf d_off, d_len, d_order, d_order_long, d_trim, d_sha, d_md5, d_scratch, d_small, d_states, d_dedupe, d_keys, d_trimctl, d_hex;
     uint64_t* h_meta = nullptr;  // pinned: offsets then lengths
     size_t h_meta_cap = 0;       // in uint64 elements
     uint64_t launches = 0;
@@ -353,9 +353,15 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     if (n >= 0x7fffffffull) return fail(ctx, B200H_E_INVALID, "batch larger than 2^31-2 messages");
     if (shared_scratch) {
         if (int rc = ensure_dev(ctx, ctx->d_order, (size_t)ring_capacity(n) * sizeof(uint32_t))) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_order_long, (size_t)kLongRingCapacity * sizeof(uint32_t))) return rc;
         if (int rc = ensure_dev(ctx, ctx->d_scratch, (kPlanScratchWords + kMaxChain) * sizeof(uint32_t))) return rc;
     }
     uint32_t* ring = shared_scratch ? (uint32_t*)ctx->d_order.p : own_ring;
+    // the long lane messages get a queue of their own (a private single-message batch never has any)
+    // (nor does a B200H_NO_OUTLIERS batch whose lengths the host does not hold: that flag promises "only enqueues",
+    // and sizing the second launch would need the planner's answer)
+    uint32_t* ring_long = (shared_scratch && !((flags & B200H_NO_OUTLIERS) && !h_len)) ? (uint32_t*)ctx->d_order_long.p : nullptr;
+    const uint32_t long_cap = ring_long ? plan_long_cap() : 0u;
     uint32_t* scratch = shared_scratch ? (uint32_t*)ctx->d_scratch.p : own_scratch;
     uint32_t* chain_list = scratch + kPlanScratchWords;
     int* qctl = plan_qctl(scratch);
@@ -367,26 +373,31 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     const bool resume = d_state != nullptr;
     const bool chain_on = ctx->chain_enabled && !(flags & B200H_NO_OUTLIERS);
     const uint32_t max_chain = chain_on ? ctx->chain_cap : 0u;
-    ctx->launches += launch_plan(len_used, n, ring, chain_list, scratch, /*fresh=*/!resume, max_chain, st);
+    ctx->launches += launch_plan(len_used, n, ring, ring_long, chain_list, scratch, /*fresh=*/!resume, max_chain, st);
+    int* qctl_long = qctl + kLongQctlAfterQctl;
     // How many outliers did the planner pick?  The count is read back (16 bytes, one stream synchronisation after
     // the ~12 us plan kernels) because a chain kernel launched "just in case" is not free: its CTAs ask for half an
     // SM's shared memory and, idle or not, skew where the lane kernel's CTAs land (1 024 x 8 MiB: 260 -> 937 ms,
     // 2 048 x 4 MiB: 159 -> 280 ms measured with a speculative launch before / after the lane kernel).
     // So: lengths known on the host -> the same selection is computed here (plan_outliers_host); otherwise read back.
-    uint32_t n_chain = 0;
-    if (chain_on) {
+    // The same goes for the long lane queue (its launch is sized on the host as well).  A batch too small to have
+    // either (nothing reaches kChainMinBlocks) needs no answer at all -- but only the host can know that.
+    uint32_t n_chain = 0, n_long = 0;
+    if (chain_on || long_cap) {
         const bool mirrored = h_len != nullptr;
-        if (mirrored) n_chain = plan_outliers_host(h_len, n, max_chain, ctx->sm_count);
+        if (mirrored) n_chain = plan_outliers_host(h_len, n, max_chain, ctx->sm_count, long_cap, &n_long);
         if (!mirrored || ctx->verify_plan) {
-            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, qctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, qctl, kPlanReadbackInts * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU_TRY(ctx, cudaStreamSynchronize(st));
             ctx->plan_syncs += 1;
-            if (mirrored && n_chain != (uint32_t)ctx->h_plan[3]) {
-                char b[128];
-                snprintf(b, sizeof b, "outlier plan mismatch: host %u, device %d", n_chain, ctx->h_plan[3]);
+            const uint32_t d_chain = (uint32_t)ctx->h_plan[3], d_long = (uint32_t)ctx->h_plan[kLongQctlAfterQctl + 3];
+            if (mirrored && (n_chain != d_chain || n_long != d_long)) {
+                char b[160];
+                snprintf(b, sizeof b, "plan mismatch: host chain %u long %u, device chain %u long %u", n_chain, n_long, d_chain, d_long);
                 return fail(ctx, B200H_E_STATE, b);
             }
-            n_chain = (uint32_t)ctx->h_plan[3];
+            n_chain = d_chain;
+            n_long = d_long;
         }
     }
     ctx->last_outliers = n_chain;
@@ -407,7 +418,14 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     // Lane CTAs leave the SMs that host a live chain CTA to the chains (they set the makespan) -- as long as enough SMs
     // stay chain-free for the lane work (chain CTAs sit on at most n_chain SMs, one each).
     const uint32_t lane_flags = (n_chain && n_chain <= ctx->sm_count * 3 / 4 && ctx->yield_chain_sms) ? (kflags | F_YIELD_CHAIN_SMS) : kflags;
-    ctx->launches += launch_lane_hash(d_base, d_off, len_used, ring, qctl, n, lane_flags, d_sha, d_md5, states, st);
+    // the short messages (dense, time-sliced), then -- same stream -- the long ones, lane-packed at one warp per SMSP
+    const uint64_t n_short = n - n_chain - n_long;
+    if (n_short)
+        ctx->launches += launch_lane_hash(d_base, d_off, len_used, ring, ring_capacity(n), qctl, qctl, n_short, lane_flags,
+                                          d_sha, d_md5, states, st);
+    if (n_long)
+        ctx->launches += launch_lane_hash(d_base, d_off, len_used, ring_long, kLongRingCapacity, qctl_long, qctl, n_long,
+                                          lane_flags, d_sha, d_md5, states, st);
     if (int rc = prof_end(ctx, st, pa, pb)) return rc;
     if (n_chain && shared_scratch) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU_TRY(ctx, cudaGetLastError());
@@ -969,7 +987,7 @@ void b200h_destroy(b200h_ctx* ctx) {
         cudaEventDestroy(pr.second);
     }
     for (DevBuf* b : {&ctx->d_off, &ctx->d_len, &ctx->d_order, &ctx->d_trim, &ctx->d_sha, &ctx->d_md5, &ctx->d_scratch,
-                      &ctx->d_small, &ctx->d_states, &ctx->d_dedupe, &ctx->d_keys, &ctx->d_trimctl, &ctx->d_hex})
+                      &ctx->d_small, &ctx->d_states, &ctx->d_dedupe, &ctx->d_keys, &ctx->d_trimctl, &ctx->d_hex, &ctx->d_order_long})
         if (b->p) cudaFree(b->p);
     for (auto& r : ctx->stream_pool) stream_res_destroy(r);
     ctx->stream_pool.clear();

@@ -464,9 +464,9 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 template <bool DO_SHA, bool DO_MD5, bool SPARSE>
 __global__ void __launch_bounds__(kLaneThreads, B200H_LANE_MIN_CTAS)
 lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
-                 uint32_t* __restrict__ ring, uint32_t ring_mask, int* __restrict__ qctl, uint32_t flags,
-                 int lanes_per_warp, uint32_t quantum, uint8_t* __restrict__ sha_out, uint8_t* __restrict__ md5_out,
-                 ChainState* __restrict__ st, uint32_t one) {
+                 uint32_t* __restrict__ ring, uint32_t ring_mask, int* __restrict__ qctl, const int* __restrict__ ctl,
+                 uint32_t flags, int lanes_per_warp, uint32_t quantum, uint8_t* __restrict__ sha_out,
+                 uint8_t* __restrict__ md5_out, ChainState* __restrict__ st, uint32_t one) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -487,7 +487,7 @@ lane_hash_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
         // happens here only, before a single message has been taken, so nothing can be stranded.
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(qctl);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(ctl);
         const uint32_t expected = ld_volatile_u32(q + kChainExpectedWord);
         if (expected) {
             const unsigned long long t0 = globaltimer_ns();
@@ -1425,12 +1425,26 @@ __host__ __device__ __forceinline__ uint32_t plan_chain_count(uint32_t count, un
     return rest <= total_blocks / 4 ? count : 0u;
 }
 
+// The LONG lane messages: those that satisfy rule (1) -- each would still be running on its lane after the rest of the
+// batch is done -- but stay on lanes (not routed to chains).  In one launch the time slicing scatters them one per warp
+// over the whole grid, and the tail then runs ~2 000 warps with a single live lane each (one rank's share of C3-v2: the
+// 12 GiB of blocks below 4 MiB took 224 ms, the 1 339 blocks of 1..4 MiB alone, lane-packed, 106 ms).  So they get
+// their own queue and a second, lane-packed launch behind the short ones.  count1 = messages satisfying rule (1).
+__host__ __device__ __forceinline__ uint32_t plan_long_count(uint32_t count1, uint32_t chain, uint32_t n, uint32_t long_cap) {
+    const uint32_t nl = count1 > chain ? count1 - chain : 0u;
+    if (nl == 0 || nl > long_cap) return 0u;     // too many to be lane-packed one wave deep: one launch as before
+    if (nl == n - chain) return 0u;              // nothing but long messages on the lanes: a single (packed) launch anyway
+    return nl;
+}
+
 // Host mirror of plan_hist_kernel + plan_scan_kernel's chain selection: how many of these messages the planner will
 // hand to the chain kernel.  Same integer arithmetic on the same lengths, so the answer is the device's; callers
 // that hold the lengths on the host use it to size the chain launch WITHOUT reading qctl[3] back (no stream
 // synchronisation inside an enqueue).  B200H_VERIFY_PLAN=1 makes the API cross-check it against the device.
-uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain, uint32_t sm_count) {
-    if (!n || !max_chain) return 0;
+uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain, uint32_t sm_count, uint32_t long_cap,
+                            uint32_t* n_long_out) {
+    *n_long_out = 0;
+    if (!n) return 0;
     uint64_t longest = 0;
     unsigned long long total = 0;
     for (uint64_t i = 0; i < n; ++i) {
@@ -1440,21 +1454,25 @@ uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain,
     if ((longest >> 6) + 1 < kChainMinBlocks) return 0;  // nothing can reach rule (1)
     unsigned long long thr = total / kChainRatio;
     if (thr < kChainMinBlocks) thr = kChainMinBlocks;
+    const unsigned long long thr1 = thr;  // rule (1) alone
     const uint32_t top = plan_bucket(longest);
     const unsigned long long half = plan_bucket_min_blocks(top) / 2;
     if (thr < half) thr = half;
     // messages in buckets whose lower bound reaches thr (bucket lower bounds are monotone in the bucket index)
-    uint64_t count = 0;
+    uint64_t count = 0, count1 = 0;
     unsigned long long chain_blocks = 0;
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t lb = plan_bucket_min_blocks(plan_bucket(len[i]));
+        if (lb >= thr1) ++count1;
         if (lb >= thr) {
             ++count;
             chain_blocks += lb;
         }
     }
-    if (count > max_chain) return 0u;
-    return plan_chain_count((uint32_t)count, chain_blocks, total, (uint32_t)n, max_chain, sm_count);
+    const uint32_t c = (max_chain && count <= max_chain)
+                           ? plan_chain_count((uint32_t)count, chain_blocks, total, (uint32_t)n, max_chain, sm_count) : 0u;
+    *n_long_out = plan_long_count((uint32_t)count1, c, (uint32_t)n, long_cap);
+    return c;
 }
 
 __global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ hist,
@@ -1495,15 +1513,16 @@ __global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, u
 // qctl = {lane entries available, head, tail, chain count}.
 __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, int* __restrict__ qctl,
                                  const unsigned long long* __restrict__ total_blocks, uint32_t n, uint32_t max_chain,
-                                 uint32_t sm_count) {
+                                 uint32_t sm_count, uint32_t long_cap) {
     __shared__ uint32_t sh[kPlanBuckets];
-    __shared__ uint32_t sh_chain, sh_top;
+    __shared__ uint32_t sh_chain, sh_top, sh_count1;
     __shared__ unsigned long long sh_chain_blocks;
     const int t = threadIdx.x;
     if (t == 0) {
         sh_chain = 0;
         sh_top = 0;
         sh_chain_blocks = 0;
+        sh_count1 = 0;
     }
     const int rev = kPlanBuckets - 1 - t;  // position in longest-first order
     sh[t] = hist[rev];
@@ -1517,6 +1536,11 @@ __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __
     cursor[rev] = sh[t] - hist[rev];  // exclusive
     unsigned long long thr = *total_blocks / kChainRatio;
     if (thr < kChainMinBlocks) thr = kChainMinBlocks;
+    {   // rule (1) alone: everything at least this long is a "long" message (chain or long lane queue)
+        const bool mine1 = plan_bucket_min_blocks((uint32_t)rev) >= thr;
+        const bool next1 = rev > 0 && plan_bucket_min_blocks((uint32_t)rev - 1) >= thr;
+        if (mine1 && !next1) atomicMax(&sh_count1, sh[t]);
+    }
     // longest non-empty bucket -> rule (2); buckets are 12.5 % wide, compare on their lower bounds
     if (hist[rev]) atomicMax(&sh_top, (uint32_t)rev);
     __syncthreads();
@@ -1528,11 +1552,17 @@ __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __
     if (mine && hist[rev]) atomicAdd(&sh_chain_blocks, (unsigned long long)hist[rev] * plan_bucket_min_blocks((uint32_t)rev));
     __syncthreads();
     if (t == 0) {
-        const uint32_t c = plan_chain_count(sh_chain, sh_chain_blocks, *total_blocks, n, max_chain, sm_count);
-        qctl[0] = (int)(n - c);  // lane-queue entries available
-        qctl[1] = 0;             // head ticket
-        qctl[2] = (int)(n - c);  // tail ticket
-        qctl[3] = (int)c;        // messages handed to the chain kernel
+        const uint32_t c = max_chain ? plan_chain_count(sh_chain, sh_chain_blocks, *total_blocks, n, max_chain, sm_count) : 0u;
+        const uint32_t nl = plan_long_count(sh_count1, c, n, long_cap);
+        qctl[0] = (int)(n - c - nl);  // lane-queue entries available (the short messages)
+        qctl[1] = 0;                  // head ticket
+        qctl[2] = (int)(n - c - nl);  // tail ticket
+        qctl[3] = (int)c;             // messages handed to the chain kernel
+        int* ql = qctl + kLongQctlAfterQctl;  // the long lane messages: their own queue
+        ql[0] = (int)nl;
+        ql[1] = 0;
+        ql[2] = (int)nl;
+        ql[3] = (int)nl;
         // qctl[4..5] hold total_blocks; [6] = chain CTAs the lane kernel may wait for, [7] = chain CTAs that started
         qctl[kChainExpectedWord] = (int)(c <= sm_count * 3 / 4 ? c : 0u);
         qctl[kChainStartedWord] = 0;
@@ -1540,9 +1570,10 @@ __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __
 }
 
 __global__ void plan_scatter_kernel(const uint64_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ cursor,
-                                    uint32_t* __restrict__ ring, uint32_t* __restrict__ chain_list,
-                                    const int* __restrict__ qctl, uint32_t tag) {
+                                    uint32_t* __restrict__ ring, uint32_t* __restrict__ ring_long,
+                                    uint32_t* __restrict__ chain_list, const int* __restrict__ qctl, uint32_t tag) {
     const uint32_t nchain = (uint32_t)qctl[3];
+    const uint32_t nlong = (uint32_t)qctl[kLongQctlAfterQctl + 3];
     // warp-aggregated atomics: lanes hitting the same bucket share one atomicAdd
     for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < n;
          i0 += (uint64_t)gridDim.x * blockDim.x) {
@@ -1557,7 +1588,8 @@ __global__ void plan_scatter_kernel(const uint64_t* __restrict__ len, uint64_t n
         if (ok) {
             const uint32_t pos = basepos + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
             if (pos < nchain) chain_list[pos] = (uint32_t)i;
-            else ring[pos - nchain] = (uint32_t)i | tag;
+            else if (pos < nchain + nlong) ring_long[pos - nchain] = (uint32_t)i | tag;
+            else ring[pos - nchain - nlong] = (uint32_t)i | tag;
         }
     }
 }
@@ -1641,6 +1673,12 @@ int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, u
 
 static int g_lane_ctas_per_sm[3] = {B200H_LANE_MIN_CTAS, B200H_LANE_MIN_CTAS, B200H_LANE_MIN_CTAS};  // [sha+md5, sha, md5]
 
+// most long messages a second, lane-packed launch takes: one wave of lanes at one warp per SMSP
+uint32_t plan_long_cap() {
+    const uint32_t cap = (uint32_t)g_sm_count * 4u * 32u;
+    return cap < kLongRingCapacity ? cap : kLongRingCapacity;
+}
+
 uint32_t ring_capacity(uint64_t n) {
     uint32_t cap = 32;
     while (cap < n) cap <<= 1;
@@ -1650,8 +1688,8 @@ uint32_t ring_capacity(uint64_t n) {
 // Builds the work lists: chain_list[0..c) = the c longest outlier messages (see plan_scan_kernel) for the chain
 // kernel; ring[0..n-c) = the rest, bucketed longest-first (tagged FRESH unless the batch resumes from
 // caller-provided chaining states), ring[n-c..cap) = EMPTY; qctl = {n-c, 0, n-c, c}.
-int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* chain_list, uint32_t* scratch, bool fresh,
-                uint32_t max_chain, cudaStream_t st) {
+int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* ring_long, uint32_t* chain_list, uint32_t* scratch,
+                bool fresh, uint32_t max_chain, cudaStream_t st) {
     const uint32_t sm_count = (uint32_t)g_sm_count;
     if (!n) return 0;
     uint32_t* hist = scratch;
@@ -1662,9 +1700,11 @@ int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* chain
     cudaMemsetAsync(reinterpret_cast<uint32_t*>(qctl) + kSmFlagsAfterQctl, 0, sizeof(uint32_t) * kSmFlagWords, st);
     cudaMemsetAsync(total, 0, sizeof(unsigned long long), st);
     cudaMemsetAsync(ring, 0xff, sizeof(uint32_t) * ring_capacity(n), st);
+    if (ring_long) cudaMemsetAsync(ring_long, 0xff, sizeof(uint32_t) * kLongRingCapacity, st);
     plan_hist_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, hist, total);
-    plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor, qctl, total, (uint32_t)n, max_chain, sm_count);
-    plan_scatter_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, cursor, ring, chain_list, qctl,
+    plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor, qctl, total, (uint32_t)n, max_chain, sm_count,
+                                                 ring_long ? plan_long_cap() : 0u);
+    plan_scatter_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, cursor, ring, ring_long, chain_list, qctl,
                                                                 fresh ? kFresh : 0u);
     return 3;
 }
@@ -1702,18 +1742,18 @@ int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* 
 
 template <bool S, bool M, bool SP>
 static void launch_lane_t(int grid, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring,
-                          uint32_t ring_mask, int* qctl, uint32_t flags, int lpw, uint32_t quantum, uint8_t* sha_out,
-                          uint8_t* md5_out, ChainState* state, cudaStream_t st) {
-    lane_hash_kernel<S, M, SP><<<grid, kLaneThreads, kLaneSmem, st>>>(base, off, len, ring, ring_mask, qctl, flags, lpw,
+                          uint32_t ring_mask, int* qctl, const int* ctl, uint32_t flags, int lpw, uint32_t quantum,
+                          uint8_t* sha_out, uint8_t* md5_out, ChainState* state, cudaStream_t st) {
+    lane_hash_kernel<S, M, SP><<<grid, kLaneThreads, kLaneSmem, st>>>(base, off, len, ring, ring_mask, qctl, ctl, flags, lpw,
                                                                 quantum, sha_out, md5_out, state, 1u);
 }
 
 // Persistent launch: at most one resident wave of CTAs; lanes pull messages from the queue until it drains.
 // When the batch has fewer messages than resident lanes, messages are spread one-per-warp first
 // (lanes_per_warp < 32) so that every chain gets its own issue slots.
-int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring, int* qctl,
-                     uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
-                     cudaStream_t st) {
+int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* ring, uint32_t ring_entries,
+                     int* qctl, const int* ctl, uint64_t n, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out,
+                     ChainState* state, cudaStream_t st) {
     if (!n) return 0;
     // Lane packing.  A warp costs the same issue slots whether 1 or 32 of its lanes carry a message, and
     // one warp alone on an SMSP is latency-bound (~0.27 IPC; measured), so: fill lanes first, but never use
@@ -1728,7 +1768,7 @@ int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* l
     int lpw = (int)((n + warps - 1) / warps);
     if (lpw > 32) lpw = 32;
     const int grid = (int)((warps + kLaneWarps - 1) / kLaneWarps);
-    const uint32_t mask = ring_capacity(n) - 1;
+    const uint32_t mask = ring_entries - 1;
     static const uint32_t quantum = [] {
         const char* e = getenv("B200H_QUANTUM");  // tuning knob (blocks per time slice)
         const long v = e ? atol(e) : 0;
@@ -1737,7 +1777,7 @@ int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* l
     const bool s = flags & F_SHA256, m = flags & F_MD5;
     // every warp alone on its SMSP -> the minimum-instruction instantiation (SHA-256 kernels; MD5 alone is latency bound)
     const bool sparse = warps <= min_warps && getenv("B200H_NO_SPARSE") == nullptr;
-#define LANE_ARGS grid, base, off, len, ring, mask, qctl, flags, lpw, quantum, sha_out, md5_out, state, st
+#define LANE_ARGS grid, base, off, len, ring, mask, qctl, ctl, flags, lpw, quantum, sha_out, md5_out, state, st
     if (s && m) {
         if (sparse) launch_lane_t<true, true, true>(LANE_ARGS);
         else launch_lane_t<true, true, false>(LANE_ARGS);

@@ -53,6 +53,9 @@ def test_host_outlier_plan_equals_device_plan(ctx):
         [100_000] * 2000,
         [80 * 1024] * 700,
         [2 << 20], [100], [0], [65536], [65535], [65536 - 64], [1 << 16] * 592, [1 << 16] * 593,
+        [3 << 20] * 344 + [1 << 20] * 995,               # more outlier candidates than 3/4 of the SMs in a mixed batch: none routed
+        [16 << 20] * 200 + [100] * 10,                   # ... unless next to nothing is left for the lanes
+        [8 << 20] * 3 + [1 << 20] * 200 + [3000] * 20000,  # chain + long lane queue + short lane queue
         list(rng.integers(0, 300_000, 900)) + [9 << 20],
         list((rng.lognormal(10, 2.0, 1500)).astype(np.int64) % (6 << 20)),
     ]
@@ -62,6 +65,25 @@ def test_host_outlier_plan_equals_device_plan(ctx):
         sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, BOTH)
         s, m, _ = c_oracle.hash_batch(buf, offs, lens)
         assert np.array_equal(sha, s) and np.array_equal(md5, m)
+
+
+def test_long_lane_messages_get_their_own_packed_launch(ctx):
+    """Mixed batch: 3 outliers (chain kernel), 200 long messages below half of the longest (they stay on lanes but in
+    their own queue: a second, lane-packed launch), 20 000 short ones.  Host plan == device plan (B200H_VERIFY_PLAN),
+    digests exact, and the launch list shows both lane launches."""
+    offs, lens = _layout([8 << 20] * 3 + [(1 << 20) + 64 * i for i in range(200)] + [3000 + (i % 977) for i in range(20000)])
+    buf = synth_array(36, int(offs[-1] + lens[-1]) + 8)
+    l0 = ctx.launch_count
+    sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, BOTH)
+    assert ctx.last_outlier_count == 3
+    assert ctx.launch_count - l0 == 3 + 1 + 2  # plan x3, chain, lane (short), lane (long)
+    s, m, _ = c_oracle.hash_batch(buf, offs, lens)
+    assert np.array_equal(sha, s) and np.array_equal(md5, m)
+    # outlier routing off: the long queue then holds the 8 MiB messages too
+    l0 = ctx.launch_count
+    sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, BOTH | _lib.NO_OUTLIERS)
+    assert ctx.last_outlier_count == 0 and ctx.launch_count - l0 == 3 + 2
+    assert np.array_equal(sha, s) and np.array_equal(md5, m)
 
 
 def test_device_batch_only_enqueues_with_host_lengths_or_no_outliers(plain_ctx):
