@@ -116,7 +116,10 @@ struct b200h_ctx {
     // One chain CTA per SM, each hosting up to chain_groups_per_cta() messages (set from the SM count at create).
     uint32_t chain_cap = 592;
     uint32_t sm_count = 148;
-    bool yield_chain_sms = true;  // B200H_YIELD_CHAIN_SMS=0: lane CTAs share SMs with chain CTAs (round-1 behaviour)
+    // B200H_YIELD_CHAIN_SMS=1: CTAs of a full-grid lane launch leave the SMs that host chain CTAs.  Off by default:
+    // measured on one rank's share of C3 (profiles/r2_c3v2_probe.md) it moved nothing (309 vs 310 ms) -- the long pole
+    // there was the lane tail, not the chains -- and it must never be applied to a small grid (see launch_lane_hash).
+    bool yield_chain_sms = false;
     int* h_plan = nullptr;        // pinned: the planner's control block {avail, head, tail, outliers} of the last batch
     uint32_t last_outliers = 0;
     bool verify_plan = false;     // B200H_VERIFY_PLAN=1: cross-check the host-side outlier count against the device's

@@ -1768,6 +1768,10 @@ int launch_lane_hash(const uint8_t* base, const uint64_t* off, const uint64_t* l
     int lpw = (int)((n + warps - 1) / warps);
     if (lpw > 32) lpw = 32;
     const int grid = (int)((warps + kLaneWarps - 1) / kLaneWarps);
+    // Leaving chain SMs is only safe when the grid fills every SM (a full resident wave): then CTAs on the chain-free
+    // SMs are guaranteed to exist and pull the work.  A small grid (a handful of CTAs, or one per SM) could land entirely
+    // on chain SMs and strand its messages -- a lone 123-byte multipart tail next to five 1 MiB parts did exactly that.
+    if (warps < resident_warps) flags &= ~F_YIELD_CHAIN_SMS;
     const uint32_t mask = ring_entries - 1;
     static const uint32_t quantum = [] {
         const char* e = getenv("B200H_QUANTUM");  // tuning knob (blocks per time slice)

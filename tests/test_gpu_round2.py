@@ -338,3 +338,17 @@ def test_hex_columns_formatted_on_the_device(plain_ctx, tmp_path):
     torch.cuda.synchronize()
     assert [bytes(r).decode() for r in h_sha.cpu().numpy()] == want_sha
     assert [bytes(r).decode() for r in h_md5.cpu().numpy()] == want_md5
+
+
+def test_small_lane_grid_next_to_chain_ctas_loses_nothing(plain_ctx):
+    """Regression (round 2): a handful of long parts on the chain kernel plus ONE short message on a one-CTA lane launch --
+    the multipart shape 5 x 1 MiB + 123 B.  A lane CTA must never step aside for a chain CTA unless other lane CTAs are
+    guaranteed to exist; repeated because CTA placement is not deterministic."""
+    offs, lens = _layout([1 << 20] * 5 + [123])
+    buf = synth_array(37, int(offs[-1] + lens[-1]) + 8)
+    s, m, _ = c_oracle.hash_batch(buf, offs, lens)
+    for flags in (BOTH, _lib.MD5, _lib.SHA256):
+        for _ in range(15):
+            sha, md5, _ = plain_ctx.hash_batch_host(buf, offs, lens, flags)
+            assert sha is None or np.array_equal(sha, s)
+            assert md5 is None or np.array_equal(md5, m)
