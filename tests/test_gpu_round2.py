@@ -68,10 +68,10 @@ def test_host_outlier_plan_equals_device_plan(ctx):
 
 
 def test_long_lane_messages_get_their_own_packed_launch(ctx):
-    """Mixed batch: 3 outliers (chain kernel), 200 long messages below half of the longest (they stay on lanes but in
+    """Mixed batch: 3 outliers (chain kernel), 100 long messages below half of the longest (they stay on lanes but in
     their own queue: a second, lane-packed launch), 20 000 short ones.  Host plan == device plan (B200H_VERIFY_PLAN),
     digests exact, and the launch list shows both lane launches."""
-    offs, lens = _layout([8 << 20] * 3 + [(1 << 20) + 64 * i for i in range(200)] + [3000 + (i % 977) for i in range(20000)])
+    offs, lens = _layout([8 << 20] * 3 + [(1 << 20) + 64 * i for i in range(100)] + [3000 + (i % 977) for i in range(20000)])  # one staging wave
     buf = synth_array(36, int(offs[-1] + lens[-1]) + 8)
     l0 = ctx.launch_count
     sha, md5, _ = ctx.hash_batch_host(buf, offs, lens, BOTH)
