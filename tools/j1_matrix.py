@@ -329,7 +329,7 @@ if "c5" in which:
         name = f"C5 size={size} ({n} messages = {n * size / GiB:.0f} GiB per GPU)"
         long_chains = size >= (1 << 28)  # chain-bound points take 4..60 s per pass: one pass, e2e on the 1-GPU run only
         dig, cap = gpu_row(name, data, offs, lens, BOTH, reps=1 if size >= (1 << 24) else 2, warm=not long_chains,
-                           e2e=(world == 1 or not long_chains), size=size, scaling="weak")
+                           e2e=(not long_chains) or (world == 1 and size < (1 << 30)), size=size, scaling="weak")
         if WITH_CPU and rank == 0:
             cpu_cap = min(CAP, CPU_PREFIX if size < (1 << 28) else CAP, 200_000 * size)
             blobs, kk = host_blobs(data, offs, lens, cpu_cap)
