@@ -376,7 +376,8 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     const bool resume = d_state != nullptr;
     const bool chain_on = ctx->chain_enabled && !(flags & B200H_NO_OUTLIERS);
     const uint32_t max_chain = chain_on ? ctx->chain_cap : 0u;
-    ctx->launches += launch_plan(len_used, n, ring, ring_long, chain_list, scratch, /*fresh=*/!resume, max_chain, st);
+    const uint32_t ratio8 = plan_ratio8(kflags);
+    ctx->launches += launch_plan(len_used, n, ring, ring_long, chain_list, scratch, /*fresh=*/!resume, max_chain, ratio8, st);
     int* qctl_long = qctl + kLongQctlAfterQctl;
     // How many outliers did the planner pick?  The count is read back (16 bytes, one stream synchronisation after
     // the ~12 us plan kernels) because a chain kernel launched "just in case" is not free: its CTAs ask for half an
@@ -388,7 +389,7 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     uint32_t n_chain = 0, n_long = 0;
     if (chain_on || long_cap) {
         const bool mirrored = h_len != nullptr;
-        if (mirrored) n_chain = plan_outliers_host(h_len, n, max_chain, ctx->sm_count, long_cap, &n_long);
+        if (mirrored) n_chain = plan_outliers_host(h_len, n, max_chain, ctx->sm_count, long_cap, ratio8, &n_long);
         if (!mirrored || ctx->verify_plan) {
             CU_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, qctl, kPlanReadbackInts * sizeof(int), cudaMemcpyDeviceToHost, st));
             CU_TRY(ctx, cudaStreamSynchronize(st));

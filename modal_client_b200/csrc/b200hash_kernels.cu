@@ -1442,7 +1442,7 @@ __host__ __device__ __forceinline__ uint32_t plan_long_count(uint32_t count1, ui
 // that hold the lengths on the host use it to size the chain launch WITHOUT reading qctl[3] back (no stream
 // synchronisation inside an enqueue).  B200H_VERIFY_PLAN=1 makes the API cross-check it against the device.
 uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain, uint32_t sm_count, uint32_t long_cap,
-                            uint32_t* n_long_out) {
+                            uint32_t ratio8, uint32_t* n_long_out) {
     *n_long_out = 0;
     if (!n) return 0;
     uint64_t longest = 0;
@@ -1456,7 +1456,7 @@ uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain,
     if (thr < kChainMinBlocks) thr = kChainMinBlocks;
     const unsigned long long thr1 = thr;  // rule (1) alone
     const uint32_t top = plan_bucket(longest);
-    const unsigned long long half = plan_bucket_min_blocks(top) / 2;
+    const unsigned long long half = plan_bucket_min_blocks(top) / 8 * ratio8;
     if (thr < half) thr = half;
     // messages in buckets whose lower bound reaches thr (bucket lower bounds are monotone in the bucket index)
     uint64_t count = 0, count1 = 0;
@@ -1513,7 +1513,7 @@ __global__ void plan_hist_kernel(const uint64_t* __restrict__ len, uint64_t n, u
 // qctl = {lane entries available, head, tail, chain count}.
 __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, int* __restrict__ qctl,
                                  const unsigned long long* __restrict__ total_blocks, uint32_t n, uint32_t max_chain,
-                                 uint32_t sm_count, uint32_t long_cap) {
+                                 uint32_t sm_count, uint32_t long_cap, uint32_t ratio8) {
     __shared__ uint32_t sh[kPlanBuckets];
     __shared__ uint32_t sh_chain, sh_top, sh_count1;
     __shared__ unsigned long long sh_chain_blocks;
@@ -1544,7 +1544,11 @@ __global__ void plan_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __
     // longest non-empty bucket -> rule (2); buckets are 12.5 % wide, compare on their lower bounds
     if (hist[rev]) atomicMax(&sh_top, (uint32_t)rev);
     __syncthreads();
-    const unsigned long long half = plan_bucket_min_blocks(sh_top) / 2;
+    // rule (2): "longer than ratio8/8 of the longest" -- what stays on a lane must finish there before the longest
+    // message finishes on its chain: lane speed / chain speed is 30/71 for the fused digests (3/8), 39/71 and 76/148
+    // for SHA-256 / MD5 alone (4/8).  (Round 1 used 1/2 throughout: the 29 MB files of C3-v1 then took 1 s on their
+    // lanes while the 59 MB file took 0.84 s on its chain.)
+    const unsigned long long half = plan_bucket_min_blocks(sh_top) / 8 * ratio8;
     if (thr < half) thr = half;
     const bool mine = plan_bucket_min_blocks((uint32_t)rev) >= thr;
     const bool next = rev > 0 && plan_bucket_min_blocks((uint32_t)rev - 1) >= thr;
@@ -1689,7 +1693,7 @@ uint32_t ring_capacity(uint64_t n) {
 // kernel; ring[0..n-c) = the rest, bucketed longest-first (tagged FRESH unless the batch resumes from
 // caller-provided chaining states), ring[n-c..cap) = EMPTY; qctl = {n-c, 0, n-c, c}.
 int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* ring_long, uint32_t* chain_list, uint32_t* scratch,
-                bool fresh, uint32_t max_chain, cudaStream_t st) {
+                bool fresh, uint32_t max_chain, uint32_t ratio8, cudaStream_t st) {
     const uint32_t sm_count = (uint32_t)g_sm_count;
     if (!n) return 0;
     uint32_t* hist = scratch;
@@ -1703,7 +1707,7 @@ int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring, uint32_t* ring_
     if (ring_long) cudaMemsetAsync(ring_long, 0xff, sizeof(uint32_t) * kLongRingCapacity, st);
     plan_hist_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, hist, total);
     plan_scan_kernel<<<1, kPlanBuckets, 0, st>>>(hist, cursor, qctl, total, (uint32_t)n, max_chain, sm_count,
-                                                 ring_long ? plan_long_cap() : 0u);
+                                                 ring_long ? plan_long_cap() : 0u, ratio8);
     plan_scatter_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(len, n, cursor, ring, ring_long, chain_list, qctl,
                                                                 fresh ? kFresh : 0u);
     return 3;

@@ -45,7 +45,7 @@ int launch_trim(const uint8_t* base, const uint64_t* off, const uint64_t* len, u
                 unsigned long long* wctl, TrimWideEntry* wlist, cudaStream_t st);
 // The planner's outlier count for these lengths, computed on the host (mirror of plan_scan_kernel's selection).
 uint32_t plan_outliers_host(const uint64_t* len, uint64_t n, uint32_t max_chain, uint32_t sm_count, uint32_t long_cap,
-                            uint32_t* n_long_out);
+                            uint32_t ratio8, uint32_t* n_long_out);
 uint32_t plan_long_cap();  // most messages the long lane queue takes (0 is passed instead when a batch has no such queue)
 uint32_t ring_capacity(uint64_t n);  // power of two >= max(n, 32): entries of the work-queue ring
 // scratch layout (uint32 words): hist[kPlanBuckets] | cursor[kPlanBuckets] | qctl[4] | total_blocks (u64) | pad
@@ -64,7 +64,8 @@ constexpr unsigned long long kYieldWaitNs = 200000;  // bound of that wait (0.2 
 // short ones are done) and ring (everything else, longest first).
 int launch_plan(const uint64_t* len, uint64_t n, uint32_t* ring /*ring_capacity(n)*/, uint32_t* ring_long /*kLongRingCapacity*/,
                 uint32_t* chain_list /*kMaxChain*/, uint32_t* scratch /*kPlanScratchWords*/, bool fresh, uint32_t max_chain,
-                cudaStream_t st);
+                uint32_t ratio8 /*rule (2): outliers are longer than ratio8/8 of the longest message*/, cudaStream_t st);
+inline uint32_t plan_ratio8(uint32_t kflags) { return ((kflags & F_SHA256) && (kflags & F_MD5)) ? 3u : 4u; }
 int launch_chain_hash(const uint8_t* base, const uint64_t* off, const uint64_t* len, const uint32_t* chain_list,
                       const int* qctl, uint32_t flags, uint8_t* sha_out, uint8_t* md5_out, ChainState* state,
                       bool resume, uint32_t n_chain /*live entries, as read back from qctl[3]*/, cudaStream_t st);
