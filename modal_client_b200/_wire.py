@@ -9,7 +9,7 @@ try:  # pragma: no cover - only with the real SDK present
     from modal_proto.api_pb2 import BlobCreateRequest, BlobGetRequest  # type: ignore
 except Exception:
 
-    @dataclasses.dataclass
+    @dataclasses.dataclass(slots=True)  # created once per map input: 10^5..10^6 per map
     class BlobCreateRequest:  # type: ignore[no-redef]
         content_md5: str = ""
         content_sha256_base64: str = ""
@@ -30,7 +30,7 @@ try:  # pragma: no cover
     from modal_proto.api_pb2 import FunctionInput, FunctionPutInputsItem, FunctionPutInputsRequest  # type: ignore
 except Exception:
 
-    @dataclasses.dataclass
+    @dataclasses.dataclass(slots=True)  # created once per map input: 10^5..10^6 per map
     class FunctionInput:  # type: ignore[no-redef]  (api.proto:2156-2165)
         args: bytes | None = None
         args_blob_id: str | None = None
@@ -38,7 +38,7 @@ except Exception:
         method_name: str | None = None
         final_input: bool = False
 
-    @dataclasses.dataclass
+    @dataclasses.dataclass(slots=True)  # created once per map input: 10^5..10^6 per map
     class FunctionPutInputsItem:  # type: ignore[no-redef]  (api.proto:2231-2237)
         idx: int = 0
         input: FunctionInput | None = None
@@ -56,7 +56,7 @@ try:  # pragma: no cover
     from modal_proto.api_pb2 import MapStartOrContinueItem  # type: ignore
 except Exception:
 
-    @dataclasses.dataclass
+    @dataclasses.dataclass(slots=True)  # created once per map input: 10^5..10^6 per map
     class MapStartOrContinueItem:  # type: ignore[no-redef]  (api.proto:2543-2546)
         input: FunctionPutInputsItem | None = None
         attempt_token: str | None = None

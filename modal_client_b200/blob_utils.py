@@ -376,20 +376,27 @@ async def _blob_upload(
 
 
 async def _blob_upload_bytes(upload_hashes: UploadHashes, data: bytes, stub) -> tuple[str, bool, int]:
-    """``_blob_upload`` for the map pump's case -- an in-memory payload whose digests came out of a GPU batch --
-    with the single-PUT branch and the provider fallback written out flat (same BlobCreate request, same fallback
-    order, same r2 bookkeeping as ``_blob_upload`` / ``_blob_upload_with_fallback``): 10^5 of these run per map on the
-    event-loop thread, and every coroutine frame and closure per input is paid there.  Anything else (multipart
-    answer, digest unknown) goes through the general function."""
-    md5_raw = getattr(upload_hashes, "md5_raw", None)
-    content_length = len(data)
-    md5_b64 = upload_hashes.md5_base64
-    resp = await stub.BlobCreate(BlobCreateRequest(content_md5=md5_b64, content_sha256_base64=upload_hashes.sha256_base64,
-                                                   content_length=content_length))
+    """``_blob_upload`` for an in-memory payload whose digests came out of a GPU batch (see ``_blob_upload_row``)."""
+    return await _blob_upload_row(upload_hashes.md5_base64, upload_hashes.sha256_base64,
+                                  getattr(upload_hashes, "md5_raw", None), data, stub)
+
+
+async def _blob_upload_row(md5_b64: str, sha256_b64: str, md5_raw: bytes | None, data: bytes, stub) -> tuple[str, bool, int]:
+    """``_blob_upload`` for the map pump's case -- an in-memory payload and its row of a GPU digest table (base64
+    columns + the raw MD5) -- with the single-PUT branch and the provider fallback written out flat (same BlobCreate
+    request, same fallback order, same r2 bookkeeping as ``_blob_upload`` / ``_blob_upload_with_fallback``): 10^5 of
+    these run per map on the event-loop thread, and every coroutine frame, closure and temporary object per input is
+    paid there.  Anything else (multipart answer, digest unknown) goes through the general function."""
+    resp = await stub.BlobCreate(BlobCreateRequest(content_md5=md5_b64, content_sha256_base64=sha256_b64,
+                                                   content_length=len(data)))  # keywords: the real class is a protobuf
     if md5_raw is None or resp.WhichOneof("upload_types_oneof") != "upload_urls":
-        return await _blob_upload(upload_hashes, data, stub, _blob_create_response=resp)
+        return await _blob_upload(hash_utils._UploadHashesRaw(md5_b64, sha256_b64, md5_raw), data, stub,
+                                  _blob_create_response=resp)
     body = KnownBytesBody(data, md5_raw)
     urls, blob_ids = resp.upload_urls.items, resp.blob_ids
+    if len(urls) == 1 and not blob_ids[0].endswith(":r2"):  # the common answer: one provider, nothing to fall back to
+        await _upload_to_s3_url(urls[0], body, content_md5_b64=md5_b64)
+        return blob_ids[0], False, 0
     r2_failed, last = False, len(urls) - 1
     for idx, url in enumerate(urls):
         blob_id = blob_ids[idx]
@@ -398,7 +405,7 @@ async def _blob_upload_bytes(upload_hashes: UploadHashes, data: bytes, stub) -> 
             if is_r2:
                 t0 = time.monotonic_ns()
                 await _upload_to_s3_url(url, body, content_md5_b64=md5_b64)
-                return blob_id, r2_failed, (content_length * 1_000_000_000) // max(time.monotonic_ns() - t0, 1)
+                return blob_id, r2_failed, (len(data) * 1_000_000_000) // max(time.monotonic_ns() - t0, 1)
             await _upload_to_s3_url(url, body, content_md5_b64=md5_b64)
             return blob_id, r2_failed, 0
         except Exception:

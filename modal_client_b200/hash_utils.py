@@ -135,9 +135,10 @@ def get_upload_hashes(
 
 
 def _b64_rows(table, width: int) -> str | None:
-    """base64 of every ``width``-byte row of a uint8[n, width] table in ONE C call: rows are zero-padded to a
-    multiple of 3 bytes, so row i occupies a fixed slice of the result whose leading characters are exactly the
-    row's own base64 without its ``=`` padding (the padding bits are zero either way)."""
+    """base64 of every ``width``-byte row of a uint8[n, width] table in ONE C call, rows back to back and each
+    complete with its ``=`` padding: rows are zero-padded to a multiple of 3 bytes, so row i occupies a fixed slice
+    of the result whose leading characters are exactly the row's own base64 (the padding bits are zero either way);
+    the characters that stand for the pad bytes are then overwritten with ``=`` for all rows at once."""
     if table is None:
         return None
     import numpy as np
@@ -146,33 +147,43 @@ def _b64_rows(table, width: int) -> str | None:
     padded = -(-width // 3) * 3
     buf = np.zeros((n, padded), np.uint8)
     buf[:, :width] = table
-    return binascii.b2a_base64(buf, newline=False).decode("ascii")
+    text = np.frombuffer(binascii.b2a_base64(buf, newline=False), np.uint8).reshape(n, padded // 3 * 4).copy()
+    if padded != width:
+        text[:, -(padded - width):] = 0x3D  # '='
+    return text.tobytes().decode("ascii")
 
 
 class _UploadHashesView(Sequence):
     """Read-only sequence of ``UploadHashes`` over a digest table; rows are formatted on access (base64 of the whole
-    table is one C call, a row is two string slices), so a batch of 10^5..10^6 payloads pays ~1 us per row."""
+    table is one C call, a row is two string slices), so a batch of 10^5..10^6 payloads pays well under 1 us per row."""
 
     def __init__(self, sha, md5, n: int):
         self._sha, self._md5, self._n = sha, md5, n
-        self._sha64 = _b64_rows(sha, 32)  # 44 chars per row: 43 significant + '='
-        self._md564 = _b64_rows(md5, 16)  # 24 chars per row: 22 significant + '=='
+        self._sha64 = _b64_rows(sha, 32)  # 44 chars per row
+        self._md564 = _b64_rows(md5, 16)  # 24 chars per row
         self._sha_bytes = sha.tobytes() if sha is not None else None
         self._md5_bytes = md5.tobytes() if md5 is not None else None
 
     def __len__(self) -> int:
         return self._n
 
+    def columns(self) -> tuple[str | None, str, bytes | None]:
+        """(md5 base64 text, 24 chars per row | None, sha256 base64 text, 44 chars per row, raw md5 bytes, 16 per row |
+        None): for callers that walk every row and do not want an object per row."""
+        return self._md564, self._sha64, self._md5_bytes
+
     def __getitem__(self, i):
-        if isinstance(i, slice):
-            return [self[j] for j in range(*i.indices(self._n))]
+        if i.__class__ is not int:
+            if isinstance(i, slice):
+                return [self[j] for j in range(*i.indices(self._n))]
+            i = int(i)
         if i < 0:
             i += self._n
         if not 0 <= i < self._n:
             raise IndexError(i)
         if self._md564 is None:
-            return _UploadHashesRaw("", self._sha64[44 * i : 44 * i + 43] + "=", None, self._sha_bytes[32 * i : 32 * i + 32])
-        return _UploadHashesRaw(self._md564[24 * i : 24 * i + 22] + "==", self._sha64[44 * i : 44 * i + 43] + "=",
+            return _UploadHashesRaw("", self._sha64[44 * i : 44 * i + 44], None, self._sha_bytes[32 * i : 32 * i + 32])
+        return _UploadHashesRaw(self._md564[24 * i : 24 * i + 24], self._sha64[44 * i : 44 * i + 44],
                                 self._md5_bytes[16 * i : 16 * i + 16], self._sha_bytes[32 * i : 32 * i + 32])
 
 

@@ -27,7 +27,7 @@ from typing import Any
 
 from . import _backend, _wire, blob_utils, hash_utils
 from ._logging import logger
-from .async_utils import bounded_map_ordered
+from .async_utils import bounded_each_ordered, bounded_map_ordered
 from . import function_utils
 from .function_utils import DevicePayload, _blob_item, _function_fields, _inline_item, serialize_data_format
 
@@ -72,7 +72,7 @@ class _WindowedInputPipeline:
         self.next_idx = first_idx
         self.first_idx = first_idx
         self.on_created = on_created or (lambda n: None)
-        self.make_item = make_item or (lambda item: item)
+        self.make_item = make_item  # None: the FunctionPutInputsItem itself
         self.windows_hashed = 0
         # where the time went (seconds): collecting+serializing, waiting for a free context, inside the GPU hash calls
         # (summed over worker threads), the upload stage waiting for a window's digests
@@ -80,35 +80,44 @@ class _WindowedInputPipeline:
         self.digest_tables: list | None = None  # set to [] to keep every window's (sha[n,32], md5[n,16]) arrays
 
     # ---- stage 1: collect ----------------------------------------------------------------------------------
-    def _take(self, win: _Window, argskwargs) -> int:
-        payload = self.serializer(argskwargs) if self.serializer else serialize_data_format(argskwargs, self.data_format)
-        nbytes = len(payload)
-        # should_upload(), written out (strictly greater than the function's limit; the 8 KiB limit for async calls)
-        if nbytes > self.max_bytes or (nbytes > blob_utils.MAX_ASYNC_OBJECT_SIZE_BYTES
-                                       and self.invocation_type == _wire.FUNCTION_CALL_INVOCATION_TYPE_ASYNC):
-            win.big.append(len(win.payloads))
-        win.payloads.append(payload)
-        self.next_idx += 1
-        self.on_created(self.next_idx - self.first_idx)
-        return nbytes
-
     async def _next_window(self) -> tuple[_Window | None, bool]:
-        """Block for one raw input, then take what is already queued, up to the byte / item budget."""
-        first = await self.q.get()
-        if first is None:
+        """Block for one raw input, then take what is already queued, up to the byte / item budget.  Every input is
+        serialized as it is taken; ``should_upload()`` is written out (strictly greater than the function's limit; the
+        8 KiB limit for async calls); ``on_created`` sees the running count after every input, like the reference's
+        ``created_callback`` (:127)."""
+        item = await self.q.get()
+        if item is None:
             return None, True
         win = _Window(self.next_idx)
-        nbytes = self._take(win, first)
-        finished = False
-        while nbytes < HASH_WINDOW_BYTES and len(win.payloads) < HASH_WINDOW_ITEMS:
-            try:
-                nxt = self.q.get_nowait()
-            except asyncio.QueueEmpty:
-                break
-            if nxt is None:
-                finished = True
-                break
-            nbytes += self._take(win, nxt)
+        payloads, big = win.payloads, win.big
+        get_nowait, serializer, data_format, on_created = self.q.get_nowait, self.serializer, self.data_format, self.on_created
+        max_bytes = self.max_bytes
+        if self.invocation_type == _wire.FUNCTION_CALL_INVOCATION_TYPE_ASYNC:
+            max_bytes = min(max_bytes, blob_utils.MAX_ASYNC_OBJECT_SIZE_BYTES)
+        serialize = serializer if serializer else (lambda it: serialize_data_format(it, data_format))
+        created = self.next_idx - self.first_idx
+        nbytes, count, finished = 0, 0, False
+        try:
+            while True:
+                payload = serialize(item)
+                n = len(payload)
+                if n > max_bytes:
+                    big.append(count)
+                payloads.append(payload)
+                nbytes += n
+                count += 1
+                on_created(created + count)
+                if nbytes >= HASH_WINDOW_BYTES or count >= HASH_WINDOW_ITEMS:
+                    break
+                try:
+                    item = get_nowait()
+                except asyncio.QueueEmpty:
+                    break
+                if item is None:
+                    finished = True
+                    break
+        finally:
+            self.next_idx += count
         return win, finished
 
     # ---- stage 2: hash -------------------------------------------------------------------------------------
@@ -170,15 +179,8 @@ class _WindowedInputPipeline:
         return hash_utils._UploadHashesView(sha, md5, n)
 
     # ---- stage 3: upload, emit in order ---------------------------------------------------------------------
-    async def run(self, emit: Callable[[Any], Any]) -> None:
-        """Drive the pipeline to the end of the input; ``emit(item)`` receives every wire item in input order and may
-        return an awaitable (a full bounded queue) that is then awaited."""
-        async for item in self.items():
-            pending = emit(item)
-            if pending is not None:
-                await pending
-
-    async def items(self):
+    async def _hashed_windows(self):
+        """(window, its UploadHashes sequence) in input order, each as soon as its hash batch is done."""
         handoff: asyncio.Queue = asyncio.Queue(maxsize=HASH_WINDOWS_IN_FLIGHT)
         producer = asyncio.ensure_future(self._collect_and_hash(handoff))
         try:
@@ -191,28 +193,69 @@ class _WindowedInputPipeline:
                 self.stats["wait_hash_s"] += time.perf_counter() - t0
                 if self.digest_tables is not None and win.hashes is not None:
                     self.digest_tables.append((hashes._sha, hashes._md5))
-                big_pos = {pos: k for k, pos in enumerate(win.big)}
-
-                async def build(pos, win=win, hashes=hashes, big_pos=big_pos):
-                    payload = win.payloads[pos]
-                    win.payloads[pos] = None  # the window must not pin every payload until its last upload is done
-                    k = big_pos.get(pos)
-                    if k is None:
-                        if type(payload) is not bytes:  # a small DevicePayload stays inline: one copy to the host
-                            payload = payload.to_bytes()
-                        return _inline_item(win.first_idx + pos, payload, self.data_format, self.method_name)
-                    if type(payload) is not bytes:
-                        payload, win.big_payloads[k] = win.big_payloads[k], None  # materialised by the hash stage
-                    upload = await blob_utils._blob_upload_bytes(hashes[k], payload, self.stub)
-                    return _blob_item(win.first_idx + pos, upload, self.data_format, self.method_name)
-
-                async for item in bounded_map_ordered(range(len(win.payloads)), build, blob_utils.BLOB_MAX_PARALLELISM):
-                    yield self.make_item(item)
+                yield win, hashes
             await producer  # surfaces a collector failure
         finally:
             if not producer.done():
                 producer.cancel()
                 await asyncio.gather(producer, return_exceptions=True)
+
+    def _builder(self, win: _Window, hashes):
+        """``build(pos)`` -> the wire item of the window's input ``pos`` (uploading its payload first if it is big)."""
+        payloads, first_idx, stub = win.payloads, win.first_idx, self.stub
+        data_format, method_name, make_item = self.data_format, self.method_name, self.make_item
+        big_pos = {pos: k for k, pos in enumerate(win.big)}
+        upload_row = blob_utils._blob_upload_row
+        # the window's digest columns, sliced per row right here (no UploadHashes object per input)
+        columns = getattr(hashes, "columns", None) if win.big else None
+        if columns is not None and columns()[0] is None:
+            columns = None  # a table without an MD5 column: rows go through the general function
+        if win.big and columns is None:  # any other sequence of UploadHashes (a caller's own hash function)
+            upload = blob_utils._blob_upload_bytes
+
+            async def build_from_objects(pos):
+                payload = payloads[pos]
+                payloads[pos] = None
+                k = big_pos.get(pos)
+                if k is None:
+                    item = _inline_item(first_idx + pos, payload, data_format, method_name)
+                else:
+                    item = _blob_item(first_idx + pos, await upload(hashes[k], payload, stub), data_format, method_name)
+                return item if make_item is None else make_item(item)
+
+            return build_from_objects
+        md5_64, sha_64, md5_raw = columns() if columns else (None, None, None)
+
+        async def build(pos):
+            payload = payloads[pos]
+            payloads[pos] = None  # the window must not pin every payload until its last upload is done
+            k = big_pos.get(pos)
+            if k is None:
+                if type(payload) is not bytes:  # a small DevicePayload stays inline: one copy to the host
+                    payload = payload.to_bytes()
+                item = _inline_item(first_idx + pos, payload, data_format, method_name)
+            else:
+                if type(payload) is not bytes:
+                    payload, win.big_payloads[k] = win.big_payloads[k], None  # materialised by the hash stage
+                up = await upload_row(md5_64[24 * k : 24 * k + 24], sha_64[44 * k : 44 * k + 44],
+                                      md5_raw[16 * k : 16 * k + 16], payload, stub)
+                item = _blob_item(first_idx + pos, up, data_format, method_name)
+            return item if make_item is None else make_item(item)
+
+        return build
+
+    async def run(self, emit: Callable[[Any], Any]) -> None:
+        """Drive the pipeline to the end of the input; ``emit(item)`` receives every wire item in input order and may
+        return an awaitable (a full bounded queue) that is then awaited."""
+        async for win, hashes in self._hashed_windows():
+            await bounded_each_ordered(len(win.payloads), self._builder(win, hashes), blob_utils.BLOB_MAX_PARALLELISM, emit)
+
+    async def items(self):
+        """The same as an async generator of wire items (the input-plane variant feeds a timestamped queue from it)."""
+        async for win, hashes in self._hashed_windows():
+            async for item in bounded_map_ordered(range(len(win.payloads)), self._builder(win, hashes),
+                                                  blob_utils.BLOB_MAX_PARALLELISM):
+                yield item
 
 
 class InputPreprocessor:
@@ -246,8 +289,9 @@ class InputPreprocessor:
         if self.keep_digest_tables:
             pipe.digest_tables = self.digest_tables
         q = self.processed_input_queue
-        # an unbounded queue (the reference's) never blocks: skip the coroutine round trip per item
-        await pipe.run(lambda item: q.put_nowait(item) if not q.full() else q.put(item))
+        # an unbounded queue (the reference's) never blocks: no fullness check, no coroutine round trip per item
+        unbounded = getattr(q, "maxsize", 1) <= 0
+        await pipe.run(q.put_nowait if unbounded else (lambda item: q.put_nowait(item) if not q.full() else q.put(item)))
         self.hash_batches = pipe.windows_hashed
         self.stats = pipe.stats
         await self.processed_input_queue.put(None)  # end-of-queue marker for the pumper
@@ -257,22 +301,28 @@ class InputPreprocessor:
 
 async def queue_batch_iterator(q: asyncio.Queue, max_batch_size: int = 100, debounce_time: float = 0.015):
     """Lists of queued items (None ends the stream); flushes early when the queue runs dry
-    (semantics of py/modal/_utils/async_utils.py:704-728)."""
+    (semantics of py/modal/_utils/async_utils.py:704-728: same batches, same debounce).  What is already queued is
+    taken with ``get_nowait`` -- one coroutine round trip per batch instead of one per item."""
     batch: list[Any] = []
+    get_nowait = getattr(q, "get_nowait", None)
     while True:
         if q.empty() and batch:
             yield batch
             batch = []
             await asyncio.sleep(debounce_time)
         item = await q.get()
-        if len(batch) >= max_batch_size:
-            yield batch
-            batch = []
-        if item is None:
-            if batch:
+        while True:
+            if len(batch) >= max_batch_size:
                 yield batch
-            return
-        batch.append(item)
+                batch = []
+            if item is None:
+                if batch:
+                    yield batch
+                return
+            batch.append(item)
+            if get_nowait is None or q.empty():
+                break
+            item = get_nowait()
 
 
 def _is_resource_exhausted(exc: BaseException) -> bool:

@@ -161,6 +161,151 @@ def test_bounded_map_ordered_streams_in_order_and_bounds_the_lookahead():
     asyncio.run(run())
 
 
+def test_bounded_each_ordered_hands_results_on_in_order_without_a_consumer_task():
+    """The map pump's upload stage: same contract as bounded_map_ordered (order, concurrency bound, look-ahead bound,
+    first failure re-raised after the results before it), results delivered by calling ``sink`` -- which may answer
+    with an awaitable (a full bounded queue) that must be awaited before the next result goes out."""
+    from modal_client_b200 import async_utils
+    from modal_client_b200.async_utils import bounded_each_ordered
+
+    async def run():
+        in_flight, peak, started = 0, 0, []
+
+        async def fn(i):
+            nonlocal in_flight, peak
+            in_flight += 1
+            peak = max(peak, in_flight)
+            started.append(i)
+            await asyncio.sleep(0.02 if i == 0 else 0.001)  # item 0 is slow: successors finish first
+            in_flight -= 1
+            return i * i
+
+        out, started_at_first = [], []
+
+        def sink(r):
+            if not out:
+                started_at_first.append(len(started))
+            out.append(r)
+
+        await bounded_each_ordered(40, fn, 4, sink)
+        assert out == [i * i for i in range(40)] and peak <= 4
+        assert started_at_first[0] <= 8 + 4  # at most 2 x concurrency results wait behind the slow one
+
+        # a sink that blocks (bounded queue): order is kept although other workers finish while it is awaited
+        q: asyncio.Queue = asyncio.Queue(maxsize=2)
+        got = []
+
+        async def consumer():
+            while True:
+                v = await q.get()
+                if v is None:
+                    return
+                await asyncio.sleep(0.0005)
+                got.append(v)
+
+        async def quick(i):
+            await asyncio.sleep(0)
+            return i
+
+        cons = asyncio.ensure_future(consumer())
+        await bounded_each_ordered(60, quick, 5, lambda r: q.put_nowait(r) if not q.full() else q.put(r))
+        await q.put(None)
+        await cons
+        assert got == list(range(60))
+
+        async def boom(i):
+            if i == 5:
+                raise RuntimeError("five")
+            return i
+
+        seen = []
+        with pytest.raises(RuntimeError, match="five"):
+            await bounded_each_ordered(20, boom, 3, seen.append)
+        assert seen == list(range(5))
+
+        def bad_sink(r):
+            if r == 3:
+                raise ValueError("sink")
+            seen2.append(r)
+
+        seen2 = []
+        with pytest.raises(ValueError, match="sink"):
+            await bounded_each_ordered(10, quick, 2, bad_sink)
+        assert seen2 == [0, 1, 2]
+        await bounded_each_ordered(0, fn, 3, seen.append)  # nothing to do
+
+        # fn that never suspends (in-process stubs) must not starve the loop: another task gets turns in between
+        ticks = 0
+
+        async def ticker():
+            nonlocal ticks
+            while True:
+                await asyncio.sleep(0)
+                ticks += 1
+
+        async def instant(i):
+            return i
+
+        tk = asyncio.ensure_future(ticker())
+        sunk = []
+        await bounded_each_ordered(2000, instant, 20, sunk.append)
+        tk.cancel()
+        assert sunk == list(range(2000)) and ticks >= 2000 // (async_utils._YIELD_EVERY * 20) - 1 >= 4
+
+    asyncio.run(run())
+
+
+def test_queue_batch_iterator_batches_like_the_reference():
+    """Same batches as py/modal/_utils/async_utils.py:704-728 for what is already queued: full batches while the queue
+    holds enough, an early flush when it runs dry, None ends the stream."""
+
+    async def reference_iter(q, max_batch_size=100, debounce_time=0.015):  # the reference's loop, restated
+        item_list = []
+        while True:
+            if q.empty() and len(item_list) > 0:
+                yield item_list
+                item_list = []
+                await asyncio.sleep(debounce_time)
+            res = await q.get()
+            if len(item_list) >= max_batch_size:
+                yield item_list
+                item_list = []
+            if res is None:
+                if len(item_list) > 0:
+                    yield item_list
+                break
+            item_list.append(res)
+
+    async def run():
+        for n, bs in ((0, 4), (1, 4), (4, 4), (5, 4), (8, 4), (9, 4), (103, 49)):
+            sizes = []
+            for it in (reference_iter, parallel_map.queue_batch_iterator):
+                q: asyncio.Queue = asyncio.Queue()
+                for i in range(n):
+                    q.put_nowait(i)
+                q.put_nowait(None)
+                batches = [b async for b in it(q, max_batch_size=bs, debounce_time=0)]
+                assert [x for b in batches for x in b] == list(range(n))
+                sizes.append([len(b) for b in batches])
+            assert sizes[0] == sizes[1], (n, bs, sizes)
+
+        # items that trickle in: a dry queue flushes what has been gathered
+        q = asyncio.Queue()
+
+        async def feed():
+            for i in range(6):
+                q.put_nowait(i)
+                await asyncio.sleep(0.004)
+            q.put_nowait(None)
+
+        f = asyncio.ensure_future(feed())
+        batches = [b async for b in parallel_map.queue_batch_iterator(q, max_batch_size=100, debounce_time=0.001)]
+        await f
+        assert [x for b in batches for x in b] == list(range(6)) and len(batches) >= 3
+
+    asyncio.run(run())
+
+
 def test_windows_are_byte_budgeted_and_items_stream_before_the_window_is_done(backend, monkeypatch):
     """the pump must not hold a whole window back -- an input reaches the processed queue as soon as its
     own upload (and its predecessors') is done -- and a window is capped by BYTES, not just by count."""
