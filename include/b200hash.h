@@ -63,6 +63,12 @@ int b200h_device_count(void);
 /* Page-locked host memory the *_host entry points can DMA from directly (no staging copy). */
 void* b200h_host_alloc(b200h_ctx* ctx, size_t bytes);
 void b200h_host_free(b200h_ctx* ctx, void* p);
+/* The staging copy the *_host entry points use to fill their pinned ring: memcpy with non-temporal stores, widest
+ * store the CPU has (AVX-512 / AVX2 / plain; picked once at run time, B200H_COPY_ISA caps the choice).  Exported for
+ * callers that fill page-locked memory from b200h_host_alloc themselves (a serializer writing its output where the
+ * DMA engine can take it) and for the CPU tests.  Needs no context and no GPU.  The reference has no counterpart. */
+void b200h_stream_copy(void* dst, const void* src, size_t n);
+const char* b200h_stream_copy_isa(void); /* "avx512" | "avx2" | "plain": what b200h_stream_copy runs on this CPU */
 
 /* ---- batch hashing ---------------------------------------------------------------------------- */
 

@@ -32,6 +32,7 @@ ABI_SYMBOLS = (
     "b200h_stream_reset", "b200h_stream_free", "b200h_fill_synth_device", "b200h_launch_count",
     "b200h_profile_enable", "b200h_profile_read", "b200h_dedupe_host", "b200h_dedupe_device",
     "b200h_last_outlier_count", "b200h_hash_batch_device_hl", "b200h_combine_stats", "b200h_plan_sync_count",
+    "b200h_stream_copy", "b200h_stream_copy_isa",
 )
 
 
@@ -41,7 +42,7 @@ class B200HashError(RuntimeError):
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in ("b200hash_kernels.cu", "b200hash_dedupe.cu", "b200hash_api.cu",
-                                            "b200blob_host.cpp", "b200hash_kernels.cuh")]
+                                            "b200blob_host.cpp", "b200pack_copy.cpp", "b200hash_kernels.cuh")]
     srcs += [os.path.join(os.path.dirname(_PKG), "include", h) for h in ("b200hash.h", "b200blob.h")]
     stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
@@ -125,6 +126,10 @@ def load_library() -> ctypes.CDLL:
         L.b200h_dedupe_host.restype = i32
         L.b200h_dedupe_device.argtypes = [vp, vp, u64, u32, vp, vp, vp]
         L.b200h_dedupe_device.restype = i32
+        L.b200h_stream_copy.argtypes = [vp, vp, sz]
+        L.b200h_stream_copy.restype = None
+        L.b200h_stream_copy_isa.argtypes = []
+        L.b200h_stream_copy_isa.restype = ctypes.c_char_p
         _lib = L
         return L
 

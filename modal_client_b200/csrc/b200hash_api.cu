@@ -440,33 +440,8 @@ int enqueue_device_batch(b200h_ctx* ctx, const uint8_t* d_base, const uint64_t* 
     return 0;
 }
 
-// memcpy into the pinned staging ring with non-temporal stores: the destination is written once and then
-// read only by the DMA engine, so bypassing the cache saves the read-for-ownership traffic of a plain
-// memcpy (3 -> 2 memory transfers per byte) and keeps the packer threads from evicting each other.
-static inline void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) {
-#if defined(__AVX2__)
-    if (n >= 4096) {
-        const size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
-        memcpy(dst, src, head);
-        dst += head; src += head; n -= head;
-        size_t i = 0;
-        for (; i + 128 <= n; i += 128) {
-            const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
-            const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
-            const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
-            const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
-            _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
-            _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
-            _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
-            _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
-        }
-        _mm_sfence();
-        memcpy(dst + i, src + i, n - i);
-        return;
-    }
-#endif
-    memcpy(dst, src, n);
-}
+// memcpy into the pinned staging ring with non-temporal stores (b200pack_copy.cpp: widest store the CPU has).
+static inline void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) { b200h_stream_copy(dst, src, n); }
 
 // Copy the packed byte range [lo, hi) of a staged wave into dst (= pinned slot, dst[0] <-> packed byte lo).
 // doff[] are the packed offsets (ascending) of messages i0..i1 inside the wave.

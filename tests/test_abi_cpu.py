@@ -45,3 +45,44 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert not re.search(r"^\s*(from|import)\s+hashlib\b", src, flags=re.M), f
+
+
+@pytest.mark.parametrize("isa", ["avx512", "avx2", "plain"])
+def test_stream_copy_is_a_memcpy_for_every_size_and_alignment(isa):
+    """b200h_stream_copy (csrc/b200pack_copy.cpp) fills the pinned staging ring of every *_host entry point: a wrong
+    byte here is a wrong digest on the GPU.  Each variant -- capped with B200H_COPY_ISA; the dispatch is decided once
+    per process, hence the subprocess -- must copy exactly n bytes for every size class (below / above the 4 KiB
+    streaming threshold, non-multiples of the unroll) and every source / destination misalignment, and must not touch
+    the bytes around the destination."""
+    import subprocess
+    import sys
+
+    code = r"""
+import ctypes, sys
+import numpy as np
+sys.path.insert(0, %r)
+from modal_client_b200 import _lib
+L = _lib.load_library()
+got = L.b200h_stream_copy_isa().decode()
+rng = np.random.default_rng(7)
+src = rng.integers(0, 256, 3 << 20, dtype=np.uint8)
+dst = np.empty(3 << 20, np.uint8)
+sizes = [0, 1, 31, 63, 64, 4095, 4096, 4097, 4096 + 127, 4096 + 128, 4096 + 255, 4096 + 256, 4096 + 257, 65536 + 3,
+         262144, 262144 + 17, 1 << 20, (1 << 20) + 255, (2 << 20) + 511]
+for n in sizes:
+    for so in (0, 1, 13, 32, 63):
+        for do in (64, 65, 77, 96, 127):
+            dst[:] = 0xA5
+            L.b200h_stream_copy(ctypes.c_void_p(dst.ctypes.data + do), ctypes.c_void_p(src.ctypes.data + so), n)
+            assert np.array_equal(dst[do:do + n], src[so:so + n]), (n, so, do)
+            assert (dst[:do] == 0xA5).all() and (dst[do + n:do + n + 512] == 0xA5).all(), (n, so, do)
+print(got)
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    env = dict(os.environ, B200H_COPY_ISA=isa)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = out.stdout.strip().splitlines()[-1]
+    assert got in ("avx512", "avx2", "plain")
+    order = ["plain", "avx2", "avx512"]
+    assert order.index(got) <= order.index(isa)  # the cap is honoured; a CPU without the ISA falls further back
+
