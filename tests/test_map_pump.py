@@ -73,6 +73,75 @@ def test_map_pump_blobifies_every_input_in_order(backend):
     asyncio.run(run())
 
 
+def test_every_blob_request_and_put_carries_the_digests_of_its_own_payload(backend, monkeypatch):
+    """Inline and blobified inputs interleaved over several windows: the row of the window's digest table that goes
+    into an input's BlobCreate request and its PUT must be that input's own (window position -> row among the big
+    payloads -> row of the table), and the items must come out in input order with the right blob ids."""
+    import base64
+
+    fn = types.SimpleNamespace(_use_method_name="", _max_object_size_bytes=3000, _metadata=object(), object_id="fu-2")
+    monkeypatch.setattr(parallel_map, "HASH_WINDOW_BYTES", 40_000)  # ~20 windows
+
+    class Stub:
+        def __init__(self):
+            self.requests = {}
+
+        async def BlobCreate(self, req):
+            blob_id = f"bl-{len(self.requests)}"
+            self.requests[blob_id] = req
+            if len(self.requests) % 3 == 0:
+                await asyncio.sleep(0.001)  # uploads finish out of order
+            return types.SimpleNamespace(WhichOneof=lambda _n: "upload_urls", blob_ids=[blob_id],
+                                         upload_urls=types.SimpleNamespace(items=[f"null://{blob_id}"]))
+
+        async def FunctionPutInputs(self, req):
+            sent.extend(req.inputs)
+
+    sent, puts = [], {}
+
+    async def put(url, payload, content_md5_b64=None, content_type=None):
+        puts[url.rsplit("/", 1)[1]] = (payload.data, content_md5_b64, payload.md5_checksum().hexdigest())
+        return "etag"
+
+    monkeypatch.setattr(blob_utils, "_upload_to_s3_url", put)
+    rng = __import__("random").Random(5)
+    payloads = [bytes([i % 251]) * rng.choice([10, 2000, 2996, 2997, 5000, 9001]) + i.to_bytes(4, "little")  # 2996 + 4 = the limit itself: stays inline for i in range(400)]
+
+    async def run():
+        stub = Stub()
+        client = types.SimpleNamespace(stub=stub)
+        raw, done = asyncio.Queue(), asyncio.Queue()
+        for p in payloads:
+            raw.put_nowait(p)
+        raw.put_nowait(None)
+        pre = parallel_map.InputPreprocessor(client, raw_input_queue=raw, processed_input_queue=done, function=fn,
+                                             serializer=lambda p: p)
+        pump = parallel_map.InputPumper(client, input_queue=done, function=fn, function_call_id="fc-2")
+
+        async def drive(gen):
+            async for _ in gen:
+                pass
+
+        await asyncio.gather(drive(pre.drain_input_generator()), drive(pump.pump_inputs()))
+        assert pre.hash_batches >= 10
+        assert [it.idx for it in sent] == list(range(len(payloads)))
+        n_blobs = 0
+        for it, p in zip(sent, payloads):
+            if len(p) <= 3000:
+                assert it.input.args == p and it.input.args_blob_id is None
+                continue
+            n_blobs += 1
+            req = stub.requests[it.input.args_blob_id]
+            body, md5_b64, md5_hex = puts[it.input.args_blob_id]
+            assert body == p and req.content_length == len(p)
+            assert req.content_md5 == md5_b64 == base64.b64encode(hashlib.md5(p).digest()).decode()
+            assert req.content_sha256_base64 == base64.b64encode(hashlib.sha256(p).digest()).decode()
+            assert md5_hex == hashlib.md5(p).hexdigest()
+        assert n_blobs == len(stub.requests) == len(puts) and 100 < n_blobs < 300
+
+    asyncio.run(run())
+
+
 def test_small_inputs_stay_inline(backend):
     fn = types.SimpleNamespace(_use_method_name="m", _max_object_size_bytes=blob_utils.MAX_OBJECT_SIZE_BYTES, _metadata=1)
 
