@@ -105,7 +105,8 @@ def test_every_blob_request_and_put_carries_the_digests_of_its_own_payload(backe
 
     monkeypatch.setattr(blob_utils, "_upload_to_s3_url", put)
     rng = __import__("random").Random(5)
-    payloads = [bytes([i % 251]) * rng.choice([10, 2000, 2996, 2997, 5000, 9001]) + i.to_bytes(4, "little")  # 2996 + 4 = the limit itself: stays inline for i in range(400)]
+    # 2996 + 4 bytes = the limit itself: stays inline; 2997 + 4 is the first size that is blobified
+    payloads = [bytes([i % 251]) * rng.choice([10, 2000, 2996, 2997, 5000, 9001]) + i.to_bytes(4, "little") for i in range(400)]
 
     async def run():
         stub = Stub()
