@@ -150,7 +150,7 @@ async def bounded_each_ordered(n: int, fn, concurrency: int, sink) -> None:
     inputs through here on the event-loop thread).  ``sink`` is a plain callable; if it returns an awaitable (a bounded
     queue that is full) that is awaited before the next result is handed on.  At most ``2 * concurrency`` finished
     results wait behind a slow predecessor.  The first failure -- of ``fn`` or ``sink`` -- cancels the rest and
-    re-raises; results before it have been delivered."""
+    re-raises; what the sink has seen by then is a prefix 0..k-1 (k <= the failing index) and nothing is handed on after it."""
     if n <= 0:
         return
     pending = object()

@@ -90,3 +90,54 @@ def test_first_occurrence_oracle_equals_numpy_unique(pool, picks):
         assert (first, nd) == ([], 0)
     assert all(f <= i and keys[f] == keys[i] for i, f in enumerate(first))
     assert sorted(set(first)) == [i for i, f in enumerate(first) if f == i]
+
+
+# ------------------------------------------------------------------ the pump's ordered, bounded upload stage
+
+@settings(max_examples=60, deadline=None)
+@given(
+    n=st.integers(0, 60),
+    concurrency=st.integers(1, 7),
+    delays=st.lists(st.integers(0, 3), min_size=60, max_size=60),
+    fail_at=st.one_of(st.none(), st.integers(0, 59)),
+    sink_blocks=st.booleans(),
+)
+def test_bounded_each_ordered_against_its_sequential_meaning(n, concurrency, delays, fail_at, sink_blocks):
+    """Whatever the completion order: results reach the sink in index order, exactly once, never more than
+    ``concurrency`` calls run at once, and after a failure at index f the sink has seen a prefix 0..k-1 with k <= f."""
+    import asyncio
+
+    from modal_client_b200.async_utils import bounded_each_ordered
+
+    async def run():
+        in_flight = peak = 0
+        out = []
+
+        async def fn(i):
+            nonlocal in_flight, peak
+            in_flight += 1
+            peak = max(peak, in_flight)
+            for _ in range(delays[i]):
+                await asyncio.sleep(0)
+            in_flight -= 1
+            if fail_at is not None and i == fail_at:
+                raise KeyError(i)
+            return i
+
+        async def slow_append(r):
+            await asyncio.sleep(0)
+            out.append(r)
+
+        sink = (lambda r: slow_append(r)) if sink_blocks else out.append
+        failed = False
+        try:
+            await bounded_each_ordered(n, fn, concurrency, sink)
+        except KeyError:
+            failed = True
+        assert peak <= concurrency
+        if fail_at is not None and fail_at < n:
+            assert failed and out == list(range(len(out))) and len(out) <= fail_at
+        else:
+            assert not failed and out == list(range(n))
+
+    asyncio.run(run())
