@@ -171,6 +171,13 @@ int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64
 /* How many messages of the most recent batch the planner handed to the outlier path (chain kernel: one CTA per
  * long message) instead of the lane kernel.  Diagnostic. */
 int b200h_last_outlier_count(b200h_ctx* ctx, uint32_t* count_out);
+/* What the planner decides for a batch with these message lengths on a device with sm_count SMs (default settings):
+ * how many messages go to the chain kernel (true outliers) and how many form the long lane queue
+ * (second, lane-packed launch).  Pure host arithmetic -- the same code that sizes the launches of
+ * b200h_hash_batch_host / _device_hl without reading the device planner's answer back -- so it needs neither a
+ * context nor a GPU.  flags: B200H_SHA256 / B200H_MD5 / B200H_NO_OUTLIERS.  Diagnostic. */
+int b200h_plan_preview(const uint64_t* lengths, uint64_t n, uint32_t flags, uint32_t sm_count, uint32_t* n_chain_out,
+                       uint32_t* n_long_out);
 /* Kernels launched by this context so far (all kinds). */
 uint64_t b200h_launch_count(b200h_ctx* ctx);
 /* Combining queue of b200h_hash_batch_host: GPU batches issued for, and caller requests served by, the small-request

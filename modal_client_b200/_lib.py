@@ -32,7 +32,7 @@ ABI_SYMBOLS = (
     "b200h_stream_reset", "b200h_stream_free", "b200h_fill_synth_device", "b200h_launch_count",
     "b200h_profile_enable", "b200h_profile_read", "b200h_dedupe_host", "b200h_dedupe_device",
     "b200h_last_outlier_count", "b200h_hash_batch_device_hl", "b200h_combine_stats", "b200h_plan_sync_count",
-    "b200h_stream_copy", "b200h_stream_copy_isa",
+    "b200h_stream_copy", "b200h_stream_copy_isa", "b200h_plan_preview",
 )
 
 
@@ -130,6 +130,8 @@ def load_library() -> ctypes.CDLL:
         L.b200h_stream_copy.restype = None
         L.b200h_stream_copy_isa.argtypes = []
         L.b200h_stream_copy_isa.restype = ctypes.c_char_p
+        L.b200h_plan_preview.argtypes = [vp, u64, u32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+        L.b200h_plan_preview.restype = i32
         _lib = L
         return L
 
@@ -143,6 +145,18 @@ _FAST_BYTES_ADDR = ctypes.string_at(id(_probe) + _BYTES_HDR, len(_probe)) == _pr
 
 def _np_ptr(a: np.ndarray | None):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def plan_preview(lengths, flags: int = SHA256 | MD5, sm_count: int = 148) -> tuple[int, int]:
+    """(messages routed to the chain kernel, messages in the long lane queue) for a batch with these lengths on a
+    device with ``sm_count`` SMs -- the library's host-side planner (no context, no GPU needed)."""
+    L = load_library()
+    ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+    c, l = ctypes.c_uint32(), ctypes.c_uint32()
+    rc = L.b200h_plan_preview(_np_ptr(ln) if ln.size else None, ln.size, flags, sm_count, ctypes.byref(c), ctypes.byref(l))
+    if rc != 0:
+        raise B200HashError(f"b200h_plan_preview failed ({rc})")
+    return c.value, l.value
 
 
 class Context:

@@ -1428,6 +1428,19 @@ int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64
     return 0;
 }
 
+int b200h_plan_preview(const uint64_t* lengths, uint64_t n, uint32_t flags, uint32_t sm_count, uint32_t* n_chain_out,
+                       uint32_t* n_long_out) {
+    if ((!lengths && n) || !sm_count || !(flags & (B200H_SHA256 | B200H_MD5)) || n >= 0x7fffffffull) return B200H_E_INVALID;
+    // the same arguments enqueue_device_batch passes for a context on such a device with the default settings
+    const uint32_t max_chain = (flags & B200H_NO_OUTLIERS) ? 0u : std::min<uint32_t>(sm_count * 4u, kMaxChain);
+    const uint32_t long_cap = std::min<uint32_t>(sm_count * 4u * 32u, kLongRingCapacity);
+    uint32_t n_long = 0;
+    const uint32_t n_chain = plan_outliers_host(lengths, n, max_chain, sm_count, long_cap, plan_ratio8(flags & 3u), &n_long);
+    if (n_chain_out) *n_chain_out = n_chain;
+    if (n_long_out) *n_long_out = n_long;
+    return 0;
+}
+
 int b200h_last_outlier_count(b200h_ctx* ctx, uint32_t* count_out) {
     if (!ctx || !count_out) return B200H_E_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
