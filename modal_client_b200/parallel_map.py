@@ -132,7 +132,7 @@ class _WindowedInputPipeline:
             def hash_window(c, payloads):
                 t = time.perf_counter()
                 try:
-                    if all(type(p) is bytes for p in payloads):
+                    if set(map(type, payloads)) == {bytes}:  # (one C-level pass: this runs on a worker thread under the GIL)
                         return hash_utils.get_upload_hashes_many(payloads, ctx=c)
                     return self._hash_mixed_window(c, payloads)
                 finally:
