@@ -276,9 +276,11 @@ class Context:
         """Hash many separate bytes-like objects without packing them in Python: their addresses go to
         the library as absolute offsets (base=NULL) and it gathers them into its pinned staging ring."""
         n = len(bufs)
-        if _FAST_BYTES_ADDR and all(type(b) is bytes for b in bufs):
-            off = np.fromiter((id(b) + _BYTES_HDR for b in bufs), dtype=np.uint64, count=n)
-            ln = np.fromiter((len(b) for b in bufs), dtype=np.uint64, count=n)
+        if _FAST_BYTES_ADDR and n and set(map(type, bufs)) == {bytes}:
+            # C-level passes only (map + fromiter): this runs on a worker thread that holds the GIL meanwhile
+            off = np.fromiter(map(id, bufs), dtype=np.uint64, count=n)
+            off += np.uint64(_BYTES_HDR)
+            ln = np.fromiter(map(len, bufs), dtype=np.uint64, count=n)
             return self.hash_batch_host(None, off, ln, flags)  # `bufs` keeps the objects alive for the call
         views = [np.frombuffer(b, dtype=np.uint8) for b in bufs]
         off = np.fromiter((v.ctypes.data if v.size else 0 for v in views), dtype=np.uint64, count=n)

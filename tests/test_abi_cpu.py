@@ -86,3 +86,27 @@ print(got)
     order = ["plain", "avx2", "avx512"]
     assert order.index(got) <= order.index(isa)  # the cap is honoured; a CPU without the ISA falls further back
 
+
+
+def test_hash_buffers_passes_the_payloads_own_addresses(monkeypatch):
+    """hash_buffers hands the library absolute addresses of the bytes objects' payloads (no copy, no numpy view per
+    payload): what it passes must read back as the payloads themselves."""
+    import ctypes
+
+    import numpy as np
+
+    seen = {}
+
+    def capture(self, base, offsets, lengths, flags=3):
+        seen["base"], seen["off"], seen["len"] = base, np.array(offsets), np.array(lengths)
+        return None, None, None
+
+    monkeypatch.setattr(_lib.Context, "hash_batch_host", capture)
+    ctx = object.__new__(_lib.Context)  # no GPU needed: only the argument marshalling is under test
+    bufs = [bytes([i % 251]) * (i * 37 % 500) + b"x" for i in range(300)]
+    ctx.hash_buffers(bufs)
+    assert seen["base"] is None and seen["off"].dtype == np.uint64 and seen["len"].dtype == np.uint64
+    assert [ctypes.string_at(int(o), int(n)) for o, n in zip(seen["off"], seen["len"])] == bufs
+    mixed = [b"abc", bytearray(b"defg"), memoryview(b"hi")]
+    ctx.hash_buffers(mixed)  # anything that is not plain bytes goes through numpy views
+    assert [ctypes.string_at(int(o), int(n)) for o, n in zip(seen["off"], seen["len"])] == [bytes(m) for m in mixed]
