@@ -35,3 +35,31 @@ def test_hbm_peak_source():
 
     peak, src = bench.hbm_peak_gbs()
     assert peak > 1000 and ("measured" in src or "fallback" in src)
+
+
+def test_e2e_leg_of_the_gpu_arm_runs_on_the_host_layer(fake_backend, monkeypatch):
+    """bench.py's headline e2e leg (run_map_pump + NullStub + _null_put) is ordinary host code around the hash call:
+    with the oracle-backed stand-in for the context it must push every payload through the real
+    InputPreprocessor / InputPumper, keep the per-window digest tables, and tell BlobCreate the digests hashlib gives."""
+    import base64
+    import hashlib
+
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from modal_client_b200 import blob_utils, parallel_map
+
+    monkeypatch.setattr(blob_utils, "_upload_to_s3_url", bench._null_put)
+    monkeypatch.setattr(parallel_map, "HASH_WINDOW_BYTES", 64 * 1024)
+    payloads = [bytes([i % 251, (i * 7) % 256]) * (1000 + 13 * i) for i in range(150)]
+    stub = bench.NullStub()
+    dt, batches, tables = bench.run_map_pump(payloads, stub)
+    assert dt > 0 and batches >= 4 and stub.inputs_put == len(payloads)
+    sha = np.concatenate([t[0] for t in tables])
+    md5 = np.concatenate([t[1] for t in tables])
+    assert [r.content_length for r in stub.blob_requests] == [len(p) for p in payloads]
+    for i, (r, p) in enumerate(zip(stub.blob_requests, payloads)):
+        assert base64.b64decode(r.content_sha256_base64) == hashlib.sha256(p).digest() == sha[i].tobytes()
+        assert base64.b64decode(r.content_md5) == hashlib.md5(p).digest() == md5[i].tobytes()
+    assert set(bench.run_map_pump.last_stats) == {"collect_s", "wait_context_s", "hash_call_s", "wait_hash_s"}
