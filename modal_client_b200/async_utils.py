@@ -7,27 +7,54 @@ import functools
 import os
 
 
-def retry(n_attempts: int = 3, base_delay: float = 0.0, delay_factor: float = 2.0):
-    """Retry an async function with exponential backoff; the last failure propagates.
-    ``RETRY_N_ATTEMPTS_OVERRIDE`` (tests) caps the attempt count, as in the reference."""
+_ATTEMPT_TIMEOUT_FLOOR = 2.0  # an attempt is never given less than this, however little of the total budget is left
 
-    def deco(fn):
+
+def retry(direct_fn=None, *, n_attempts: int = 3, base_delay: float = 0.0, delay_factor: float = 2.0,
+          max_delay: float | None = None, attempt_timeout: float | None = 90, total_timeout: float | None = None):
+    """Decorator: call an async function up to ``n_attempts`` times; the last failure propagates.
+
+    Same knobs and behaviour as the reference's helper (py/modal/_utils/async_utils.py:345-433), which the upload path
+    uses as ``@retry(n_attempts=3, base_delay=0.3, attempt_timeout=None)`` (blob_utils.py:110) and
+    ``@retry(n_attempts=5, base_delay=0.1, attempt_timeout=None)`` (:377): between attempts it sleeps ``base_delay``,
+    growing by ``delay_factor`` each time and capped at ``max_delay``; each attempt runs under
+    ``asyncio.wait_for(attempt_timeout)`` (None: no limit); with ``total_timeout`` the attempt's limit also shrinks to
+    what is left of the overall budget (never below 2 s) and a retry whose sleep would run past the budget is not
+    made.  Cancellation is never retried.  ``RETRY_N_ATTEMPTS_OVERRIDE`` (environment; tests) replaces
+    ``n_attempts``.  Usable bare (``@retry``) or with arguments."""
+    import time
+
+    def decorate(fn):
         @functools.wraps(fn)
-        async def wrapped(*args, **kwargs):
-            attempts = int(os.environ.get("RETRY_N_ATTEMPTS_OVERRIDE", n_attempts))
-            delay = base_delay
+        async def attempt_loop(*args, **kwargs):
+            override = os.environ.get("RETRY_N_ATTEMPTS_OVERRIDE")
+            attempts = int(override) if override else n_attempts
+            deadline = None if total_timeout is None else time.time() + total_timeout
+            pause = base_delay
             for attempt in range(attempts):
+                limit = attempt_timeout
+                if deadline is not None:
+                    left = max(deadline - time.time(), _ATTEMPT_TIMEOUT_FLOOR)
+                    limit = left if limit is None else min(limit, left)
                 try:
-                    return await fn(*args, **kwargs)
+                    if limit is None:
+                        return await fn(*args, **kwargs)
+                    return await asyncio.wait_for(fn(*args, **kwargs), timeout=limit)
+                except asyncio.CancelledError:
+                    raise
                 except Exception:
                     if attempt == attempts - 1:
                         raise
-                    await asyncio.sleep(delay)
-                    delay *= delay_factor
+                    if deadline is not None and time.time() + pause + _ATTEMPT_TIMEOUT_FLOOR >= deadline:
+                        raise  # the budget would be gone after the sleep: fail now instead of sleeping first
+                await asyncio.sleep(pause)
+                pause *= delay_factor
+                if max_delay is not None:
+                    pause = min(pause, max_delay)
 
-        return wrapped
+        return attempt_loop
 
-    return deco
+    return decorate(direct_fn) if direct_fn is not None else decorate
 
 
 @contextlib.asynccontextmanager

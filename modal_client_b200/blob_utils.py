@@ -154,7 +154,7 @@ def _with_view(fp: BinaryIO, fn):
 # ------------------------------------------------------------------------------------ single-part PUT
 
 
-@retry(n_attempts=3, base_delay=0.3)
+@retry(n_attempts=3, base_delay=0.3, attempt_timeout=None)
 async def _upload_to_s3_url(
     upload_url,
     payload,
@@ -470,7 +470,7 @@ async def blob_upload_file(
 # ------------------------------------------------------------------------------------------- download
 
 
-@retry(n_attempts=5, base_delay=0.1)
+@retry(n_attempts=5, base_delay=0.1, attempt_timeout=None)
 async def _download_from_url(download_url: str) -> bytes:
     """GET one blob (reference :377-388; no integrity check there either: blobs are addressed by id)."""
     async with ClientSessionRegistry.get_session().get(download_url) as s3_resp:

@@ -216,7 +216,7 @@ async def _put_missing_blocks(file_specs, missing_blocks, put_responses: dict[by
         waiting.add(mb.block_index)
         report = functools.partial(progress_cb, task_id=task_id)
 
-        @retry(n_attempts=11, base_delay=0.5)
+        @retry(n_attempts=11, base_delay=0.5, attempt_timeout=None)  # reference: volume.py:1542
         async def attempt(payload) -> bytes:
             with payload.reset_on_error(subtract_progress=True):
                 async with ClientSessionRegistry.get_session().put(mb.put_url, data=payload) as resp:

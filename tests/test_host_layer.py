@@ -423,3 +423,71 @@ def test_batched_specs_hash_the_bytes_they_cache_and_redo_files_that_grew(fake_b
     assert sum(1 for r in reads if r.endswith("small.bin")) == 1, "the cached file must be read exactly once"
     assert specs[1].size == 300_000 and specs[1].sha256_hex == hashlib.sha256(b"g" * 300_000).hexdigest()
     assert specs[1].md5_hex == hashlib.md5(b"g" * 300_000).hexdigest()
+
+
+# ------------------------------------------------------------------------- async helpers of the upload path
+
+
+def test_retry_counts_attempts_like_the_reference(monkeypatch):
+    """Cases of py/test/async_utils_test.py:75-121: default 3 attempts, n_attempts=5, the bare-decorator form, the
+    delay sequence base * factor^k capped at max_delay, the per-attempt timeout, RETRY_N_ATTEMPTS_OVERRIDE."""
+    import asyncio
+
+    from modal_client_b200 import async_utils
+    from modal_client_b200.async_utils import retry
+
+    class Boom(Exception):
+        pass
+
+    def fail_n_times(n):
+        calls = {"n": 0}
+
+        async def fn(x):
+            calls["n"] += 1
+            if calls["n"] <= n:
+                raise Boom(calls["n"])
+            return x + 1
+
+        return fn
+
+    async def run():
+        assert await retry(fail_n_times(2))(42) == 43  # bare form, 3 attempts
+        with pytest.raises(Boom):
+            await retry(fail_n_times(3))(42)
+        assert await retry(n_attempts=5)(fail_n_times(4))(42) == 43
+        with pytest.raises(Boom):
+            await retry(n_attempts=5)(fail_n_times(5))(42)
+
+        delays = []
+        real_sleep = asyncio.sleep
+
+        async def fake_sleep(d):
+            delays.append(d)
+            await real_sleep(0)
+
+        monkeypatch.setattr(async_utils.asyncio, "sleep", fake_sleep)
+        try:
+            fn = retry(n_attempts=5, base_delay=1, delay_factor=2, max_delay=2, attempt_timeout=None)(fail_n_times(4))
+            assert await fn(0) == 1 and delays == [1, 2, 2, 2]
+        finally:
+            monkeypatch.setattr(async_utils.asyncio, "sleep", real_sleep)
+
+        @retry(n_attempts=2, attempt_timeout=0.01)
+        async def hangs():
+            await asyncio.sleep(1)
+
+        with pytest.raises(asyncio.TimeoutError):
+            await hangs()
+
+        @retry(n_attempts=3)
+        async def cancelled():
+            raise asyncio.CancelledError()
+
+        with pytest.raises(asyncio.CancelledError):
+            await cancelled()
+
+        monkeypatch.setenv("RETRY_N_ATTEMPTS_OVERRIDE", "1")
+        with pytest.raises(Boom):
+            await retry(n_attempts=5)(fail_n_times(1))(0)
+
+    asyncio.run(run())
