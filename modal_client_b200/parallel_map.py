@@ -283,6 +283,28 @@ class InputPreprocessor:
         self.inputs_created = n
         self.created_callback(n)
 
+    async def input_iter(self):
+        """The raw inputs one by one until the end-of-input sentinel (reference :113-118)."""
+        while True:
+            raw_input = await self.raw_input_queue.get()
+            if raw_input is None:
+                break
+            yield raw_input
+
+    def create_input_factory(self):
+        """The reference's per-input form (:120-135): ``await create_input((args, kwargs))`` numbers the input, reports
+        it and builds its item on its own -- one hash launch per blobified input.  ``drain_input_generator`` does not
+        use it (it batches); it is here for callers that drive inputs themselves."""
+
+        async def create_input(argskwargs):
+            idx = self.inputs_created
+            self._created(idx + 1)
+            args, kwargs = argskwargs
+            return await function_utils._create_input(args, kwargs, self.client.stub, idx=idx, function=self.function,
+                                                      serializer=(lambda ak: self.serializer(ak)) if self.serializer else None)
+
+        return create_input
+
     async def drain_input_generator(self):
         pipe = _WindowedInputPipeline(self.raw_input_queue, self.client.stub, self.function, first_idx=0,
                                       on_created=self._created, serializer=self.serializer)

@@ -160,8 +160,12 @@ class VolumeUploadContextManager(_BatchBase):
 class VolumeUploadContextManager2(_BatchBase):
     """volumefs2 batch upload: all 8 MiB blocks of all queued files form one GPU batch (trim scan + SHA-256)."""
 
-    def __init__(self, volume_id: str, client, progress_cb=None, force: bool = False, put_concurrency: int = 128):
+    def __init__(self, volume_id: str, client, progress_cb=None, force: bool = False,
+                 hash_concurrency: int | None = None, put_concurrency: int = 128):
         super().__init__(volume_id, client, progress_cb, force)
+        # the reference hashes blocks under a semaphore of ``hash_concurrency`` = cpu_count executor threads
+        # (volume.py:1358,1383); here every block of every file is one GPU batch, so the knob is accepted and unused
+        self._hash_concurrency = hash_concurrency
         self._put_concurrency = put_concurrency
 
     async def __aexit__(self, exc_type, exc_val, exc_tb):
@@ -245,3 +249,37 @@ async def _put_missing_blocks(file_specs, missing_blocks, put_responses: dict[by
         missing = [mb for i, mb in enumerate(missing) if first[i] == i]
     for digest, resp in await bounded_map(missing, put_one, concurrency=put_concurrency):
         put_responses[digest] = resp
+
+
+# ---------------------------------------------------------------------------------- the reference's names
+
+# enum VolumeFsVersion, modal_proto/api.proto:312-316
+VOLUME_FS_VERSION_UNSPECIFIED, VOLUME_FS_VERSION_V1, VOLUME_FS_VERSION_V2 = 0, 1, 2
+
+
+class _AbstractVolumeUploadContextManager:
+    """The interface ``Volume.batch_upload`` hands out, and the version switch behind it (py/modal/volume.py:1137-1173)."""
+
+    async def __aenter__(self): ...
+
+    async def __aexit__(self, exc_type, exc_val, exc_tb): ...
+
+    def put_file(self, local_file, remote_path, mode=None): ...
+
+    def put_directory(self, local_path, remote_path, recursive=True): ...
+
+    @staticmethod
+    def resolve(version, object_id: str, client, progress_cb: Callable[..., Any] | None = None, force: bool = False):
+        if version in (None, VOLUME_FS_VERSION_UNSPECIFIED, VOLUME_FS_VERSION_V1):
+            return VolumeUploadContextManager(object_id, client, progress_cb=progress_cb, force=force)
+        if version == VOLUME_FS_VERSION_V2:
+            return VolumeUploadContextManager2(object_id, client, progress_cb=progress_cb, force=force)
+        raise RuntimeError(f"unsupported volume version: {version}")
+
+
+# The reference keeps the implementation under the underscore name and exports a synchronicity wrapper under the plain
+# one; there is no wrapper layer here, so both names mean the class itself.
+AbstractVolumeUploadContextManager = _AbstractVolumeUploadContextManager
+_VolumeUploadContextManager = VolumeUploadContextManager
+_VolumeUploadContextManager2 = VolumeUploadContextManager2
+

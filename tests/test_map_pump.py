@@ -629,3 +629,32 @@ def test_pump_hashes_cuda_tensor_payloads_in_hbm(gpu_backend):
     items, blobs, requests = _run_pump_with_device_payloads(make, raw_bytes)
     _check_device_payload_run(items, blobs, requests, raw_bytes)
     assert gpu_backend.launch_count > launches0
+
+
+def test_per_input_form_of_the_preprocessor(backend):
+    """``input_iter`` / ``create_input_factory`` of the reference's InputPreprocessor (py/modal/parallel_map.py:113-135):
+    inputs are numbered from 0 in call order, ``created_callback`` sees the running count, small inputs stay inline and
+    big ones are blobified -- the same items the batched ``drain_input_generator`` produces."""
+    fn = types.SimpleNamespace(_use_method_name="", _max_object_size_bytes=2000, _metadata=object(), object_id="fu-3")
+
+    async def run():
+        async with running_blob_server() as (host, store):
+            client = types.SimpleNamespace(stub=FakeBlobStub(host, multipart_threshold=10**9))
+            raw = asyncio.Queue()
+            inputs = [((i,), {"pad": "y" * (i * 900)}) for i in range(5)]
+            for ak in inputs:
+                raw.put_nowait(ak)
+            raw.put_nowait(None)
+            created = []
+            pre = parallel_map.InputPreprocessor(client, raw_input_queue=raw, processed_input_queue=asyncio.Queue(),
+                                                 function=fn, created_callback=created.append)
+            create_input = pre.create_input_factory()
+            items = [await create_input(ak) async for ak in pre.input_iter()]
+            assert [it.idx for it in items] == [0, 1, 2, 3, 4] and created == [1, 2, 3, 4, 5] and pre.inputs_created == 5
+            for it, ak in zip(items, inputs):
+                blob = it.input.args_blob_id
+                assert pickle.loads(store.blobs[blob] if blob else it.input.args) == ak
+            assert [bool(it.input.args_blob_id) for it in items] == [False, False, False, True, True]
+            await blob_utils.ClientSessionRegistry.close_session()
+
+    asyncio.run(run())

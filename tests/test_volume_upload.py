@@ -216,3 +216,18 @@ def test_put_directory_walk_selects_what_rglob_is_file_selects(tmp_path):
     batch = volume._BatchBase("vo", client=None)
     batch.put_directory(str(root), PurePosixPath("/dst/"), recursive=True)  # str source, trailing slash on the remote
     assert sorted(r for _, r, _ in batch._paths) == sorted(r for _, r in reference_way(True))
+
+
+def test_resolve_picks_the_uploader_by_filesystem_version():
+    """py/modal/volume.py:1156-1173: unspecified / v1 -> the volumefs1 uploader, v2 -> the volumefs2 uploader,
+    anything else is an error; the reference's underscore names resolve to the same classes."""
+    from modal_client_b200 import volume as v
+
+    for version in (None, v.VOLUME_FS_VERSION_UNSPECIFIED, v.VOLUME_FS_VERSION_V1):
+        m = v._AbstractVolumeUploadContextManager.resolve(version, "vo-1", client=None, force=True)
+        assert type(m) is v._VolumeUploadContextManager and m._volume_id == "vo-1" and m._force
+    m2 = v.AbstractVolumeUploadContextManager.resolve(v.VOLUME_FS_VERSION_V2, "vo-2", client=None)
+    assert type(m2) is v._VolumeUploadContextManager2 and m2._put_concurrency == 128
+    assert v._VolumeUploadContextManager2("vo-3", None, hash_concurrency=7, put_concurrency=3)._put_concurrency == 3
+    with pytest.raises(RuntimeError, match="unsupported volume version"):
+        v._AbstractVolumeUploadContextManager.resolve(99, "vo", client=None)
