@@ -3,8 +3,8 @@
 // The destination is written once and then read only by the GPU's copy engine, so the copy uses non-temporal
 // stores: no read-for-ownership of the destination lines (2 instead of 3 memory transfers per byte) and the packer
 // threads do not evict each other's source lines.  The widest store the CPU has is picked once at run time
-// (AVX-512 64-byte stores where available: +13..20 % per thread over 32-byte stores on Sapphire Rapids, measured with
-// the harness described in DESIGN.md 5.9; AVX2 otherwise; plain memcpy on anything older).  This file is host-only
+// (AVX-512 64-byte stores where available: +10..14 % per thread over 32-byte stores on Sapphire Rapids, measured with
+// tools/copybench.cpp; AVX2 otherwise; plain memcpy on anything older).  This file is host-only
 // C++ (compiled by the host compiler, not by cudafe++), which is why it can carry per-function target attributes.
 //
 // Replaces nothing in the reference (it has no staging); it is the first stage of b200h_hash_batch_host /
