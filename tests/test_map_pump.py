@@ -371,7 +371,7 @@ def test_queue_batch_iterator_batches_like_the_reference():
         f = asyncio.ensure_future(feed())
         batches = [b async for b in parallel_map.queue_batch_iterator(q, max_batch_size=100, debounce_time=0.001)]
         await f
-        assert [x for b in batches for x in b] == list(range(6)) and len(batches) >= 3
+        assert [x for b in batches for x in b] == list(range(6)) and len(batches) >= 2
 
     asyncio.run(run())
 
