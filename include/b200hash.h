@@ -171,6 +171,13 @@ int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64
 /* How many messages of the most recent batch the planner handed to the outlier path (chain kernel: one CTA per
  * long message) instead of the lane kernel.  Diagnostic. */
 int b200h_last_outlier_count(b200h_ctx* ctx, uint32_t* count_out);
+/* The staging step of b200h_hash_batch_host on its own: gather n messages (base may be NULL with absolute addresses in
+ * offsets[]) into dst the way a wave is laid out in HBM -- message i at the next multiple of 16, offsets returned
+ * through packed_offsets_out -- with the library's packer team of `threads` threads working slot_bytes at a time (the
+ * size of a pinned slot).  dst needs sum((len + 15) & ~15) bytes.  No context, no GPU: for the CPU tests of the packer
+ * and for measuring a host's packing rate (tools/packbench.py).  Diagnostic. */
+int b200h_pack_preview(const uint8_t* base, const uint64_t* offsets, const uint64_t* lengths, uint64_t n, uint8_t* dst,
+                       uint64_t dst_bytes, uint64_t slot_bytes, int threads, uint64_t* packed_offsets_out);
 /* What the planner decides for a batch with these message lengths on a device with sm_count SMs (default settings):
  * how many messages go to the chain kernel (true outliers) and how many form the long lane queue
  * (second, lane-packed launch).  Pure host arithmetic -- the same code that sizes the launches of

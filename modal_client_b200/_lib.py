@@ -32,7 +32,7 @@ ABI_SYMBOLS = (
     "b200h_stream_reset", "b200h_stream_free", "b200h_fill_synth_device", "b200h_launch_count",
     "b200h_profile_enable", "b200h_profile_read", "b200h_dedupe_host", "b200h_dedupe_device",
     "b200h_last_outlier_count", "b200h_hash_batch_device_hl", "b200h_combine_stats", "b200h_plan_sync_count",
-    "b200h_stream_copy", "b200h_stream_copy_isa", "b200h_plan_preview",
+    "b200h_stream_copy", "b200h_stream_copy_isa", "b200h_plan_preview", "b200h_pack_preview",
 )
 
 
@@ -132,6 +132,8 @@ def load_library() -> ctypes.CDLL:
         L.b200h_stream_copy_isa.restype = ctypes.c_char_p
         L.b200h_plan_preview.argtypes = [vp, u64, u32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
         L.b200h_plan_preview.restype = i32
+        L.b200h_pack_preview.argtypes = [vp, vp, vp, u64, vp, u64, u64, i32, vp]
+        L.b200h_pack_preview.restype = i32
         _lib = L
         return L
 
@@ -157,6 +159,24 @@ def plan_preview(lengths, flags: int = SHA256 | MD5, sm_count: int = 148) -> tup
     if rc != 0:
         raise B200HashError(f"b200h_plan_preview failed ({rc})")
     return c.value, l.value
+
+
+def pack_preview(base, offsets, lengths, threads: int = 16, slot_bytes: int = 256 << 20, dst: np.ndarray | None = None):
+    """(packed uint8 buffer, packed offsets uint64[n]): the staging step of the *_host entry points on its own -- the
+    messages gathered by the library's packer team into the layout a wave has in HBM.  ``base`` may be None with
+    absolute addresses in ``offsets``.  No context, no GPU."""
+    L = load_library()
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+    need = int(((ln + np.uint64(15)) & ~np.uint64(15)).sum()) if ln.size else 0
+    if dst is None:
+        dst = np.empty(max(need, 1), np.uint8)
+    out = np.empty(max(ln.size, 1), np.uint64)
+    bp = None if base is None else ctypes.c_void_p(np.asarray(base).ctypes.data)
+    rc = L.b200h_pack_preview(bp, _np_ptr(off), _np_ptr(ln), ln.size, _np_ptr(dst), dst.size, slot_bytes, threads, _np_ptr(out))
+    if rc != 0:
+        raise B200HashError(f"b200h_pack_preview failed ({rc})")
+    return dst, out[: ln.size]
 
 
 class Context:

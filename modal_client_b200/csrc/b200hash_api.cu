@@ -506,6 +506,14 @@ void pack_range(const Source& src, const uint64_t* len, const uint64_t* doff, ui
     if (fd >= 0) close(fd);
 }
 
+// Fill dst with the packed byte range [lo, hi) using up to `threads` threads.  The range is cut into grains (>= 1 MiB,
+// about eight per thread) that the threads take from a shared counter: with a static split the slot is only as fast as
+// its slowest thread, and the packers share their cores with the DMA set-up, Python threads, a second context's team
+// and, under torchrun, the other ranks' teams.  (Build machine, a shared 8-core VM, scattered 256 KiB sources into
+// 256 MiB slots, best of three runs: two teams of 8 threads at once 44.6 -> 48.1 GiB/s, two teams of 16 39.6 -> 43.6,
+// two teams of 4 53.0 -> 55.5; a lone team of 8 swung between 12 and 24 GiB/s with the static split and 17 and 41 with
+// grains while a neighbour was busy;
+// profiles/r2_stream_copy_build_machine.txt.)  The calling thread works too, so a team of t costs t - 1 thread starts.
 void pack_parallel(int threads, const Source& src, const uint64_t* len, const uint64_t* doff, uint64_t i0, uint64_t i1,
                    uint64_t lo, uint64_t hi, uint8_t* dst, const cpu_set_t* cpus = nullptr) {
     const uint64_t bytes = hi - lo;
@@ -517,13 +525,24 @@ void pack_parallel(int threads, const Source& src, const uint64_t* len, const ui
         pack_range(src, len, doff, i0, i1, lo, hi, dst);
         return;
     }
+    const uint64_t grain = std::max<uint64_t>(uint64_t(1) << 20, (bytes / ((uint64_t)t * 8) + 4095) & ~uint64_t(4095));
+    const uint64_t grains = (bytes + grain - 1) / grain;
+    std::atomic<uint64_t> next{0};
+    auto work = [&] {
+        for (;;) {
+            const uint64_t g = next.fetch_add(1, std::memory_order_relaxed);
+            if (g >= grains) return;
+            const uint64_t a = lo + g * grain, b = std::min(hi, a + grain);
+            pack_range(src, len, doff, i0, i1, a, b, dst + (a - lo));
+        }
+    };
     std::vector<std::thread> th;
-    th.reserve(t);
-    for (int k = 0; k < t; ++k) {
-        const uint64_t a = lo + bytes * k / t, b = lo + bytes * (k + 1) / t;
-        th.emplace_back([=, &src] { pack_range(src, len, doff, i0, i1, a, b, dst + (a - lo)); });
+    th.reserve(t - 1);
+    for (int k = 0; k < t - 1; ++k) {
+        th.emplace_back(work);
         if (cpus) pthread_setaffinity_np(th.back().native_handle(), sizeof(cpu_set_t), cpus);  // best effort
     }
+    work();
     for (auto& x : th) x.join();
 }
 
@@ -1425,6 +1444,29 @@ int b200h_fill_synth_device(b200h_ctx* ctx, void* d_dst, uint64_t nbytes, uint64
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->s_comp;
     ctx->launches += launch_fill_synth((uint8_t*)d_dst, nbytes, seed, start, st);
     CU_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+int b200h_pack_preview(const uint8_t* base, const uint64_t* offsets, const uint64_t* lengths, uint64_t n, uint8_t* dst,
+                       uint64_t dst_bytes, uint64_t slot_bytes, int threads, uint64_t* packed_offsets_out) {
+    if ((!offsets || !lengths) && n) return B200H_E_INVALID;
+    if (!dst || threads < 1 || slot_bytes < 4096) return B200H_E_INVALID;
+    // the layout a staged wave gets in hash_batch_host_impl: every message at the next multiple of 16
+    std::vector<uint64_t> doff(n ? n : 1);
+    uint64_t used = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        doff[i] = used;
+        used += (lengths[i] + 15) & ~15ull;
+    }
+    if (used > dst_bytes) return B200H_E_INVALID;
+    Source src;
+    src.base = base;
+    src.off = offsets;
+    // ... filled slot by slot, as the pinned ring is
+    for (uint64_t lo = 0; lo < used; lo += slot_bytes)
+        pack_parallel(threads, src, lengths, doff.data(), 0, n, lo, std::min(used, lo + slot_bytes), dst + lo);
+    if (packed_offsets_out)
+        for (uint64_t i = 0; i < n; ++i) packed_offsets_out[i] = doff[i];
     return 0;
 }
 

@@ -110,3 +110,36 @@ def test_hash_buffers_passes_the_payloads_own_addresses(monkeypatch):
     mixed = [b"abc", bytearray(b"defg"), memoryview(b"hi")]
     ctx.hash_buffers(mixed)  # anything that is not plain bytes goes through numpy views
     assert [ctypes.string_at(int(o), int(n)) for o, n in zip(seen["off"], seen["len"])] == [bytes(m) for m in mixed]
+
+
+@pytest.mark.parametrize("threads,slot_mib", [(1, 32), (2, 8), (3, 13), (8, 32), (16, 64)])
+def test_packer_team_gathers_every_message_to_its_place(threads, slot_mib):
+    """b200h_pack_preview runs the packer team of the *_host entry points (pack_parallel: grains handed out from a shared
+    counter) without a GPU.  Whatever the team size and slot size, every message must land byte for byte at its packed
+    offset (next multiple of 16), across grain and slot boundaries, for empty, tiny and multi-MiB messages, unaligned
+    sources, and both addressing forms (base + offset, absolute addresses)."""
+    import numpy as np
+
+    rng = np.random.default_rng(threads * 100 + slot_mib)
+    lens = np.concatenate([
+        rng.integers(0, 64, 200), rng.integers(64, 70_000, 400), rng.integers(200_000, 3_000_000, 40),
+        [0, 1, 15, 16, 17, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 5 << 20],
+    ]).astype(np.uint64)
+    rng.shuffle(lens)
+    gaps = rng.integers(0, 40, lens.size).astype(np.uint64)
+    offs = (np.concatenate([[0], np.cumsum(lens + gaps)])[:-1] + np.uint64(3)).astype(np.uint64)
+    src = rng.integers(0, 256, int(offs[-1] + lens[-1]) + 64, dtype=np.uint8)
+    packed, doff = _lib.pack_preview(src, offs, lens, threads=threads, slot_bytes=slot_mib << 20)
+    expect_off = np.concatenate([[0], np.cumsum((lens + np.uint64(15)) & ~np.uint64(15))])[:-1].astype(np.uint64)
+    assert np.array_equal(doff, expect_off)
+    for i in range(lens.size):
+        a, n, s = int(doff[i]), int(lens[i]), int(offs[i])
+        assert np.array_equal(packed[a:a + n], src[s:s + n]), i
+    # absolute addresses (what hash_buffers passes for Python bytes objects)
+    packed2, doff2 = _lib.pack_preview(None, offs + np.uint64(src.ctypes.data), lens, threads=threads, slot_bytes=slot_mib << 20)
+    assert np.array_equal(doff2, doff)
+    for i in range(0, lens.size, 7):
+        a, n = int(doff[i]), int(lens[i])
+        assert np.array_equal(packed2[a:a + n], packed[a:a + n])
+    with pytest.raises(_lib.B200HashError):
+        _lib.pack_preview(src, offs, lens, threads=threads, dst=np.empty(1024, np.uint8))  # destination too small
