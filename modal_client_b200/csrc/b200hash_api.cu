@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <string>
@@ -33,6 +34,7 @@
 
 #include "../../include/b200hash.h"
 #include "b200hash_kernels.cuh"
+#include "b200pack_team.h"
 
 using namespace b200h;
 
@@ -156,6 +158,7 @@ struct b200h_ctx {
     uint64_t prof_n = 0;
     int pack_threads = 1;
     int io_threads = 1;
+    PackTeam team;  // the packer / reader threads (used under `mu` only)
     // CPUs of the NUMA node the GPU hangs off (empty set: unknown / single node / B200H_NUMA=0).  The packer and
     // reader threads are pinned there: the staging ring lives in that node's memory and the DMA engine reads it from
     // there, so a packer on the other socket would push every byte across the socket interconnect twice.
@@ -513,9 +516,9 @@ void pack_range(const Source& src, const uint64_t* len, const uint64_t* doff, ui
 // 256 MiB slots, best of three runs: two teams of 8 threads at once 44.6 -> 48.1 GiB/s, two teams of 16 39.6 -> 43.6,
 // two teams of 4 53.0 -> 55.5; a lone team of 8 swung between 12 and 24 GiB/s with the static split and 17 and 41 with
 // grains while a neighbour was busy;
-// profiles/r2_stream_copy_build_machine.txt.)  The calling thread works too, so a team of t costs t - 1 thread starts.
-void pack_parallel(int threads, const Source& src, const uint64_t* len, const uint64_t* doff, uint64_t i0, uint64_t i1,
-                   uint64_t lo, uint64_t hi, uint8_t* dst, const cpu_set_t* cpus = nullptr) {
+// profiles/r2_stream_copy_build_machine.txt.)  The threads are the context's PackTeam; the calling thread works too.
+void pack_parallel(PackTeam& team, int threads, const Source& src, const uint64_t* len, const uint64_t* doff, uint64_t i0,
+                   uint64_t i1, uint64_t lo, uint64_t hi, uint8_t* dst, const cpu_set_t* cpus = nullptr) {
     const uint64_t bytes = hi - lo;
     // memory sources: one thread per >= 4 MiB; file sources: syscalls dominate small files, so also split by count
     uint64_t want = bytes / (4u << 20);
@@ -536,14 +539,7 @@ void pack_parallel(int threads, const Source& src, const uint64_t* len, const ui
             pack_range(src, len, doff, i0, i1, a, b, dst + (a - lo));
         }
     };
-    std::vector<std::thread> th;
-    th.reserve(t - 1);
-    for (int k = 0; k < t - 1; ++k) {
-        th.emplace_back(work);
-        if (cpus) pthread_setaffinity_np(th.back().native_handle(), sizeof(cpu_set_t), cpus);  // best effort
-    }
-    work();
-    for (auto& x : th) x.join();
+    team.run(t, cpus, work);
 }
 
 int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint64_t n,
@@ -688,10 +684,10 @@ int hash_batch_host_impl(b200h_ctx* ctx, const uint8_t* base, const uint64_t* of
                 if (pin_used[pin_slot]) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_pin[pin_slot]));
                 const cpu_set_t* cpus = ctx->node_cpus_valid ? &ctx->node_cpus : nullptr;
                 if (w.seg)
-                    pack_parallel(paths ? ctx->io_threads : ctx->pack_threads, seg_src, &seg_len1, &seg_doff1, 0, 1, lo, hi,
+                    pack_parallel(ctx->team, paths ? ctx->io_threads : ctx->pack_threads, seg_src, &seg_len1, &seg_doff1, 0, 1, lo, hi,
                                   ctx->pin[pin_slot], cpus);
                 else
-                    pack_parallel(paths ? ctx->io_threads : ctx->pack_threads, src, len, doff, w.i0, w.i1, lo, hi,
+                    pack_parallel(ctx->team, paths ? ctx->io_threads : ctx->pack_threads, src, len, doff, w.i0, w.i1, lo, hi,
                                   ctx->pin[pin_slot], cpus);
                 if (io_errno.load()) {
                     const int e = io_errno.load();
@@ -1462,9 +1458,11 @@ int b200h_pack_preview(const uint8_t* base, const uint64_t* offsets, const uint6
     Source src;
     src.base = base;
     src.off = offsets;
-    // ... filled slot by slot, as the pinned ring is
+    // ... filled slot by slot, as the pinned ring is, by a team that outlives the call like a context's does (one per
+    // calling thread here: a context's team is protected by the context mutex, this one by being thread-local)
+    static thread_local PackTeam team;
     for (uint64_t lo = 0; lo < used; lo += slot_bytes)
-        pack_parallel(threads, src, lengths, doff.data(), 0, n, lo, std::min(used, lo + slot_bytes), dst + lo);
+        pack_parallel(team, threads, src, lengths, doff.data(), 0, n, lo, std::min(used, lo + slot_bytes), dst + lo);
     if (packed_offsets_out)
         for (uint64_t i = 0; i < n; ++i) packed_offsets_out[i] = doff[i];
     return 0;

@@ -143,3 +143,38 @@ def test_packer_team_gathers_every_message_to_its_place(threads, slot_mib):
         assert np.array_equal(packed2[a:a + n], packed[a:a + n])
     with pytest.raises(_lib.B200HashError):
         _lib.pack_preview(src, offs, lens, threads=threads, dst=np.empty(1024, np.uint8))  # destination too small
+
+
+def test_packer_team_survives_many_slots_and_concurrent_callers():
+    """The packer threads are started once and parked between slots (PackTeam): hundreds of wake-ups, a team that grows
+    between calls, and several callers at once (each with its own team, like contexts) must neither lose a byte nor hang."""
+    import threading
+
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    lens = rng.integers(100_000, 400_000, 600).astype(np.uint64)  # ~150 MB
+    offs = np.concatenate([[0], np.cumsum(lens + np.uint64(5))])[:-1].astype(np.uint64)
+    src = rng.integers(0, 256, int(offs[-1] + lens[-1]) + 16, dtype=np.uint8)
+    expect_off = np.concatenate([[0], np.cumsum((lens + np.uint64(15)) & ~np.uint64(15))])[:-1]
+    errors = []
+
+    def caller(seed):
+        try:
+            for rep in range(6):
+                threads = [2, 5, 8, 3, 16, 4][(rep + seed) % 6]
+                packed, doff = _lib.pack_preview(src, offs, lens, threads=threads, slot_bytes=(8 + 8 * ((rep + seed) % 3)) << 20)
+                assert np.array_equal(doff, expect_off)
+                for i in range(seed % 7, lens.size, 7):
+                    a, n, s = int(doff[i]), int(lens[i]), int(offs[i])
+                    assert np.array_equal(packed[a:a + n], src[s:s + n]), (seed, rep, i)
+        except BaseException as exc:  # noqa: BLE001 - reported by the main thread
+            errors.append(exc)
+
+    ths = [threading.Thread(target=caller, args=(k,)) for k in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=240)
+    assert not any(t.is_alive() for t in ths), "a packer team hung"
+    assert not errors, errors[0]

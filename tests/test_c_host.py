@@ -127,3 +127,23 @@ def test_napi_addon_hashes_many_matches_node_crypto_semantics(napi_exe):
         assert out["sha256"][i] == base64.b64encode(hashlib.sha256(data).digest()).decode()
     assert out["should_upload_2MiB"] is False and out["should_upload_2MiB_plus_1"] is True
     assert out["throws_on_non_array"] is True
+
+
+@pytest.mark.parametrize("sanitize", [False, True], ids=["plain", "tsan"])
+def test_packer_team_hands_every_grain_out_exactly_once(tmp_path, sanitize):
+    """modal_client_b200/csrc/b200pack_team.h (the parked packer / reader threads of a context) driven by
+    tests/c/pack_team_check.cpp: thousands of jobs of the grain-counter kind, changing team sizes, clean shutdown --
+    once as a plain build, once under ThreadSanitizer (skipped where the toolchain has no libtsan)."""
+    out = str(tmp_path / "pack_team_check")
+    cmd = ["g++", "-std=c++17", "-pthread", "-Wall", "-Wextra", "-Werror"]
+    cmd += ["-O1", "-g", "-fsanitize=thread"] if sanitize else ["-O2"]
+    cmd += [os.path.join(ROOT, "tests", "c", "pack_team_check.cpp"), "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if sanitize and r.returncode != 0 and ("tsan" in r.stderr.lower() or "sanitize" in r.stderr.lower()):
+        pytest.skip("ThreadSanitizer runtime not available: " + r.stderr.strip().splitlines()[-1])
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([out, "2000" if sanitize else "20000"], capture_output=True, text=True, timeout=600)
+    if sanitize and "FATAL: ThreadSanitizer" in r.stderr:  # e.g. an address-space layout the runtime refuses
+        pytest.skip(r.stderr.strip().splitlines()[0])
+    assert r.returncode == 0 and "PACK TEAM OK" in r.stdout, r.stdout + r.stderr
+    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
