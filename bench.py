@@ -282,6 +282,11 @@ def run_gpu(args) -> None:
     from modal_client_b200 import _backend, _lib, batch, blob_utils, parallel_map, sharding
 
     rank, world, local_rank = env_rank()
+    # a run that is still going after 13 minutes is hung (a normal one takes about one): say where, and end it,
+    # instead of holding the box until somebody else's limit kills it silently
+    import faulthandler
+
+    faulthandler.dump_traceback_later(int(os.environ.get("B200H_BENCH_WATCHDOG_S", 780)), exit=True)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     all_cpus = os.sched_getaffinity(0)
@@ -536,6 +541,7 @@ def run_gpu(args) -> None:
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
 
 
 def main():
