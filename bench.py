@@ -522,7 +522,7 @@ def run_gpu(args) -> None:
             "cpu_baseline": cpu,
             "e2e": {"value": round(pump_value, 3), "unit": "GiB/s", "h2d_bytes_per_step": total_bytes + 16 * N_MSG,
                     "d2h_bytes_per_step": 56 * N_MSG, "steps": e2e_steps,
-                    "api": "parallel_map.InputPreprocessor -> hash_utils.get_upload_hashes_many -> blob_utils._blob_upload "
+                    "api": "parallel_map.InputPreprocessor -> hash_utils.get_upload_hashes_many -> blob_utils._blob_upload_row "
                            "-> parallel_map.InputPumper over 100 000 pageable Python bytes (wire-format inputs, identity "
                            "serializer), null BlobCreate / PUT / FunctionPutInputs"
                            + (" + sharding.all_gather_table (NCCL)" if world > 1 else ""),
